@@ -1,0 +1,35 @@
+#!/usr/bin/env bash
+# Builds the REFERENCE's own sources for the hot path, from where they lie under
+# /root/reference (read-only), into oracle/_ref/ (git-ignored, travels to the GPU box).
+# No reference source is copied into the repo: the Cython NMS needs a 2-token numpy-2
+# patch (np.int_t -> np.intp_t, np.int -> np.intp), which is applied by
+# sed into a temp dir at build time.
+#   _ref/libroialign_ref.so       <- lib/cppcuda_cffi/src/cpp/roi_align_cpu_loop.cpp   (CPU loop)
+#   _ref/libroialign_ref_cuda.so  <- lib/cppcuda_cffi/src/cuda/roi_align_forward_cuda_kernel.cu
+#                                     (the reference CUDA kernel, compiled unmodified for sm_100a:
+#                                      the on-box "kernel to beat")
+#   _ref/cython_nms*.so           <- lib/utils_cython/cython_nms.pyx (patched as above)
+set -euo pipefail
+REF=${REF:-/root/reference}
+HERE=$(cd "$(dirname "$0")" && pwd)
+OUT=$HERE/_ref
+if [ ! -d "$REF/lib" ]; then echo "build_ref: $REF not present (GPU box) - using prebuilt $OUT"; exit 0; fi
+mkdir -p "$OUT"
+g++ -O2 -fPIC -shared -o "$OUT/libroialign_ref.so" "$REF/lib/cppcuda_cffi/src/cpp/roi_align_cpu_loop.cpp"
+if command -v nvcc >/dev/null; then
+  nvcc -O3 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -shared \
+       -o "$OUT/libroialign_ref_cuda.so" "$REF/lib/cppcuda_cffi/src/cuda/roi_align_forward_cuda_kernel.cu"
+fi
+TMP=$(mktemp -d)
+sed -e 's/np\.int_t/np.intp_t/g' -e 's/dtype=np\.int)/dtype=np.intp)/g' \
+    "$REF/lib/utils_cython/cython_nms.pyx" > "$TMP/cython_nms.pyx"
+cat > "$TMP/setup.py" <<'PY'
+from setuptools import setup, Extension
+from Cython.Build import cythonize
+import numpy as np
+setup(ext_modules=cythonize([Extension("cython_nms", ["cython_nms.pyx"], include_dirs=[np.get_include()],
+      extra_compile_args=["-O2", "-Wno-cpp"])], language_level=2, quiet=True))
+PY
+(cd "$TMP" && python setup.py -q build_ext --inplace >/dev/null 2>&1 && cp cython_nms*.so "$OUT/")
+rm -rf "$TMP"
+ls -la "$OUT"

@@ -1,0 +1,306 @@
+"""
+ORACLE -- test infrastructure only.  Never imported by the product path
+(detectorch_b200/).  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module.
+
+CPU restatement of the reference's host-side hot-path logic (numpy where the
+reference uses numpy, torch-CPU where the reference uses torch, so the fp32
+results are bit-identical to the reference run on CPU):
+
+  generate_anchors            lib/utils/generate_anchors.py:54-122
+  generate_proposals_level    lib/model/generate_proposals.py:31-238
+  nms                         lib/utils/boxes.py:332-336 -> lib/utils_cython/cython_nms.pyx:37-87
+  map_rois_to_fpn_levels      lib/utils/multilevel_rois.py:41-53
+  collect_and_distribute      lib/model/collect_and_distribute_fpn_rpn_proposals.py:84-128
+  multilevel_rois_for_test    lib/utils/multilevel_rois.py:19-82
+  bbox_transform / clip       lib/utils/boxes.py:150-208
+  box_results_with_nms_and_limit / postprocess_output   lib/utils/result_utils.py:76-168
+  roi_align_forward           lib/cppcuda_cffi/src/cpp/roi_align_cpu_loop.cpp:118-224 (oracle/roi_align_ref.c)
+
+Parity pinned: tests/test_oracle.py checks every function here against (a) the
+reference's own modules imported from /root/reference when that tree is
+present (this container) and (b) the committed vectors in tests/golden/
+generated from the reference by tests/golden/make_golden.py.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+BBOX_XFORM_CLIP = 4.135166556742356  # boxes.py:73 / generate_proposals.py:165
+
+
+def build():
+    """Compile the C restatement (oracle/liboracle.so) and, when /root/reference is
+    present, the reference's own sources into oracle/_ref/ (build_ref.sh)."""
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+    subprocess.check_call(["bash", os.path.join(_HERE, "build_ref.sh")], stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            subprocess.check_call(["make", "-s", "-C", _HERE])
+        _lib = ctypes.CDLL(path)
+        _lib.oracle_nms.restype = ctypes.c_int64
+    return _lib
+
+
+def _fp(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+# ----------------------------------------------------------------------------- RoIAlign
+def roi_align_forward(features, rois, pooled_h, pooled_w, spatial_scale, sampling_ratio):
+    """features [B,C,H,W] fp32, rois [R,4|5] fp32 -> [R,C,ph,pw] fp32 (numpy)."""
+    f = np.ascontiguousarray(np.asarray(features, dtype=np.float32))
+    r = np.ascontiguousarray(np.asarray(rois, dtype=np.float32))
+    B, C, H, W = f.shape
+    R, cols = r.shape
+    out = np.zeros((R, C, pooled_h, pooled_w), np.float32)
+    lib().oracle_roi_align_forward(_fp(f), _fp(r), ctypes.c_int64(R), ctypes.c_int(cols),
+                                   ctypes.c_int(C), ctypes.c_int(H), ctypes.c_int(W),
+                                   ctypes.c_int(pooled_h), ctypes.c_int(pooled_w),
+                                   ctypes.c_float(spatial_scale), ctypes.c_int(sampling_ratio), _fp(out))
+    return out
+
+
+def roi_align_forward_ref(features, rois, pooled_h, pooled_w, spatial_scale, sampling_ratio):
+    """Same through the reference's own compiled loop (oracle/_ref/libroialign_ref.so)."""
+    so = ctypes.CDLL(os.path.join(_HERE, "_ref", "libroialign_ref.so"))
+    f = np.ascontiguousarray(np.asarray(features, dtype=np.float32))
+    r = np.ascontiguousarray(np.asarray(rois, dtype=np.float32))
+    B, C, H, W = f.shape
+    R, cols = r.shape
+    out = np.zeros((R, C, pooled_h, pooled_w), np.float32)
+    so.roi_align_forward_loop(ctypes.c_int(out.size), _fp(f), _fp(r), ctypes.c_float(spatial_scale),
+                              ctypes.c_int(C), ctypes.c_int(H), ctypes.c_int(W), ctypes.c_int(pooled_h),
+                              ctypes.c_int(pooled_w), ctypes.c_int(sampling_ratio), ctypes.c_int(cols), _fp(out))
+    return out
+
+
+# ----------------------------------------------------------------------------- NMS
+def nms(dets, thresh):
+    """dets [N,5] fp32 (x1,y1,x2,y2,score) -> ascending original indices kept (int64).
+    boxes.py:332-336: empty input returns []."""
+    dets = np.ascontiguousarray(np.asarray(dets, dtype=np.float32))
+    n = dets.shape[0]
+    if n == 0:
+        return np.zeros((0,), np.int64)
+    order = np.ascontiguousarray(dets[:, 4].argsort()[::-1].astype(np.int64))   # pyx:45
+    keep = np.empty((n,), np.int64)
+    k = lib().oracle_nms(_fp(dets), _fp(order), ctypes.c_int64(n), ctypes.c_float(thresh), _fp(keep))
+    return keep[:k].copy()
+
+
+# ----------------------------------------------------------------------------- anchors
+def generate_anchors(stride=16, sizes=(32, 64, 128, 256, 512), aspect_ratios=(0.5, 1, 2)):
+    """(A,4) float64 anchor table; rows ordered ratio-major, size-minor.
+    generate_anchors.py:54-122 (ratio enumeration with np.round, then scales)."""
+    base = float(stride)
+    scales = np.asarray(sizes, dtype=np.float64) / stride
+    ratios = np.asarray(aspect_ratios, dtype=np.float64)
+    # reference window (0,0,base-1,base-1): w=h=base, centre (base-1)/2
+    w0 = h0 = base
+    cx = cy = 0.5 * (base - 1)
+    rows = []
+    area = w0 * h0
+    for r in ratios:
+        wr = np.round(np.sqrt(area / r))
+        hr = np.round(wr * r)
+        for s in scales:
+            ws, hs = wr * s, hr * s
+            rows.append([cx - 0.5 * (ws - 1), cy - 0.5 * (hs - 1), cx + 0.5 * (ws - 1), cy + 0.5 * (hs - 1)])
+    return np.asarray(rows, dtype=np.float64)
+
+
+def all_anchors(anchors, feat_h, feat_w, spatial_scale):
+    """generate_proposals.py:124-149: shifted anchors in (H,W,A) order, float64."""
+    stride = 1. / spatial_scale
+    sx = np.arange(0, feat_w) * stride
+    sy = np.arange(0, feat_h) * stride
+    sx, sy = np.meshgrid(sx, sy)
+    shifts = np.stack([sx.ravel(), sy.ravel(), sx.ravel(), sy.ravel()], axis=1)
+    return (anchors[None, :, :] + shifts[:, None, :]).reshape(-1, 4)
+
+
+# ----------------------------------------------------------------------------- proposals
+def _decode_torch(boxes, deltas, weights=(1.0, 1.0, 1.0, 1.0)):
+    """generate_proposals.py:165-214 (torch fp32 arithmetic, columns x1,y1,x2,y2)."""
+    widths = boxes[:, 2] - boxes[:, 0] + 1.0
+    heights = boxes[:, 3] - boxes[:, 1] + 1.0
+    ctr_x = boxes[:, 0] + 0.5 * widths
+    ctr_y = boxes[:, 1] + 0.5 * heights
+    wx, wy, ww, wh = weights
+    dx, dy = deltas[:, 0::4] / wx, deltas[:, 1::4] / wy
+    dw, dh = deltas[:, 2::4] / ww, deltas[:, 3::4] / wh
+    clip = torch.tensor([BBOX_XFORM_CLIP], dtype=torch.float32)
+    dw, dh = torch.min(dw, clip), torch.min(dh, clip)
+    pcx = dx * widths.unsqueeze(1) + ctr_x.unsqueeze(1)
+    pcy = dy * heights.unsqueeze(1) + ctr_y.unsqueeze(1)
+    pw = torch.exp(dw) * widths.unsqueeze(1)
+    ph = torch.exp(dh) * heights.unsqueeze(1)
+    return torch.cat((pcx - 0.5 * pw, pcy - 0.5 * ph, pcx + 0.5 * pw - 1, pcy + 0.5 * ph - 1), 1)
+
+
+def generate_proposals_level(rpn_cls_prob, rpn_bbox_pred, im_h, im_w, scaling_factor, spatial_scale,
+                             anchor_sizes, aspect_ratios=(0.5, 1, 2), pre_nms_top_n=6000, post_nms_top_n=1000,
+                             nms_thresh=0.7, min_size=0, return_stages=False):
+    """One image, one level.  rpn_cls_prob [1,A,H,W], rpn_bbox_pred [1,4A,H,W] (torch CPU fp32).
+    generate_proposals.py:31-122.  Returns (proposals [n,4], scores [n,1]) torch fp32;
+    with return_stages also a dict of the integer stages (order, filter keep, nms keep)."""
+    anchors = generate_anchors(stride=1. / spatial_scale, sizes=anchor_sizes, aspect_ratios=aspect_ratios)
+    A = anchors.shape[0]
+    H, W = rpn_cls_prob.shape[2], rpn_cls_prob.shape[3]
+    anc_np = all_anchors(anchors, H, W, spatial_scale)
+    anc = torch.FloatTensor(anc_np)                                               # :55 float64 -> fp32
+    deltas = rpn_bbox_pred.squeeze(0).permute(1, 2, 0).contiguous().view(-1, 4)    # :64
+    scores = rpn_cls_prob.squeeze(0).permute(1, 2, 0).contiguous().view(-1, 1)     # :72
+    s_np = scores.numpy()
+    if pre_nms_top_n <= 0 or pre_nms_top_n >= len(s_np):
+        order = np.argsort(-s_np.squeeze())                                        # :78
+    else:
+        inds = np.argpartition(-s_np.squeeze(), pre_nms_top_n)[:pre_nms_top_n]      # :82-84
+        order = inds[np.argsort(-s_np[inds].squeeze())]
+    deltas, scores, anc = deltas[order, :], scores[order, :], anc[order, :]
+    s_np = s_np[order, :]
+    props = _decode_torch(anc, deltas)                                             # :96
+    lim_w = torch.tensor([float(im_w)]) - 1
+    lim_h = torch.tensor([float(im_h)]) - 1
+    z = torch.tensor([0.0])
+    props[:, 0::4] = torch.max(torch.min(props[:, 0::4], lim_w), z)                # :231-237
+    props[:, 1::4] = torch.max(torch.min(props[:, 1::4], lim_h), z)
+    props[:, 2::4] = torch.max(torch.min(props[:, 2::4], lim_w), z)
+    props[:, 3::4] = torch.max(torch.min(props[:, 3::4], lim_h), z)
+    p_np = props.numpy()
+    ms = min_size * scaling_factor                                                 # :155
+    ws = p_np[:, 2] - p_np[:, 0] + 1
+    hs = p_np[:, 3] - p_np[:, 1] + 1
+    xc = p_np[:, 0] + ws / 2.
+    yc = p_np[:, 1] + hs / 2.
+    fkeep = np.where((ws >= ms) & (hs >= ms) & (xc < im_w) & (yc < im_h))[0]        # :160-162
+    props, scores = props[fkeep, :], scores[fkeep, :]
+    p_np, s_np = p_np[fkeep, :], s_np[fkeep]
+    nkeep = None
+    if nms_thresh > 0:
+        nkeep = nms(np.hstack((p_np, s_np)), nms_thresh)                           # :115
+        if post_nms_top_n > 0:
+            nkeep = nkeep[:post_nms_top_n]
+        props, scores = props[nkeep, :], scores[nkeep, :]
+    if return_stages:
+        return props, scores, {"order": order, "filter_keep": fkeep, "nms_keep": nkeep}
+    return props, scores
+
+
+# ----------------------------------------------------------------------------- FPN level mapping
+def boxes_area(boxes):
+    return (boxes[:, 2] - boxes[:, 0] + 1) * (boxes[:, 3] - boxes[:, 1] + 1)        # boxes.py:75-81
+
+
+def map_rois_to_fpn_levels(rois, k_min, k_max, s0=224, lvl0=4):
+    """multilevel_rois.py:41-53 (numpy, dtype of `rois` preserved: fp32 in the detector)."""
+    s = np.sqrt(boxes_area(rois))
+    lv = np.floor(lvl0 + np.log2(s / s0 + 1e-6))
+    return np.clip(lv, k_min, k_max)
+
+
+def collect_and_distribute(roi_list, score_list, lvl_min=2, lvl_max=5, post_nms_top_n=1000):
+    """collect...py:84-128.  roi_list: per-level torch [n_l,4]; score_list: [n_l,1].
+    Returns (per-level roi tensors, idx_restore int64 numpy, collected rois [n,4], lvls)."""
+    rois = torch.cat(tuple(roi_list), 0)
+    scores = torch.cat(tuple(score_list), 0).squeeze()
+    _, inds = torch.sort(-scores)                                                  # :102
+    rois = rois[inds[:post_nms_top_n], :]
+    lvls = map_rois_to_fpn_levels(rois.numpy(), lvl_min, lvl_max)
+    order = np.empty((0,))
+    per_level = []
+    for lvl in range(lvl_min, lvl_max + 1):
+        idx = np.where(lvls == lvl)[0]
+        per_level.append(rois[idx, :])
+        order = np.concatenate((order, idx))
+    return per_level, np.argsort(order), rois, lvls
+
+
+def multilevel_rois_for_test(rois, lvl_min=2, lvl_max=5):
+    """multilevel_rois.py:19-82: numpy rois [n,4] -> (per-level arrays, idx_restore int32)."""
+    lvls = map_rois_to_fpn_levels(rois, lvl_min, lvl_max)
+    order = np.empty((0,))
+    per_level = []
+    for lvl in range(lvl_min, lvl_max + 1):
+        idx = np.where(lvls == lvl)[0]
+        per_level.append(rois[idx, :])
+        order = np.concatenate((order, idx))
+    return per_level, np.argsort(order).astype(np.int32)
+
+
+# ----------------------------------------------------------------------------- detection post-processing
+def bbox_transform(boxes, deltas, weights=(1.0, 1.0, 1.0, 1.0)):
+    """boxes.py:168-208 (numpy)."""
+    if boxes.shape[0] == 0:
+        return np.zeros((0, deltas.shape[1]), dtype=deltas.dtype)
+    boxes = boxes.astype(deltas.dtype, copy=False)
+    w = boxes[:, 2] - boxes[:, 0] + 1.0
+    h = boxes[:, 3] - boxes[:, 1] + 1.0
+    cx = boxes[:, 0] + 0.5 * w
+    cy = boxes[:, 1] + 0.5 * h
+    wx, wy, ww, wh = weights
+    dx, dy = deltas[:, 0::4] / wx, deltas[:, 1::4] / wy
+    dw = np.minimum(deltas[:, 2::4] / ww, BBOX_XFORM_CLIP)
+    dh = np.minimum(deltas[:, 3::4] / wh, BBOX_XFORM_CLIP)
+    pcx = dx * w[:, None] + cx[:, None]
+    pcy = dy * h[:, None] + cy[:, None]
+    pw = np.exp(dw) * w[:, None]
+    ph = np.exp(dh) * h[:, None]
+    out = np.zeros(deltas.shape, dtype=deltas.dtype)
+    out[:, 0::4] = pcx - 0.5 * pw
+    out[:, 1::4] = pcy - 0.5 * ph
+    out[:, 2::4] = pcx + 0.5 * pw - 1
+    out[:, 3::4] = pcy + 0.5 * ph - 1
+    return out
+
+
+def clip_tiled_boxes(boxes, im_shape):
+    """boxes.py:150-165."""
+    boxes[:, 0::4] = np.maximum(np.minimum(boxes[:, 0::4], im_shape[1] - 1), 0)
+    boxes[:, 1::4] = np.maximum(np.minimum(boxes[:, 1::4], im_shape[0] - 1), 0)
+    boxes[:, 2::4] = np.maximum(np.minimum(boxes[:, 2::4], im_shape[1] - 1), 0)
+    boxes[:, 3::4] = np.maximum(np.minimum(boxes[:, 3::4], im_shape[0] - 1), 0)
+    return boxes
+
+
+def box_results_with_nms_and_limit(scores, boxes, num_classes=81, score_thresh=0.05, overlap_thresh=0.5,
+                                   max_detections_per_img=100):
+    """result_utils.py:96-168 (hard-NMS branch; soft-NMS / voting are off by default)."""
+    cls_boxes = [[] for _ in range(num_classes)]
+    for j in range(1, num_classes):
+        inds = np.where(scores[:, j] > score_thresh)[0]
+        dets_j = np.hstack((boxes[inds, j * 4:(j + 1) * 4], scores[inds, j][:, None])).astype(np.float32, copy=False)
+        keep = nms(dets_j, overlap_thresh)
+        cls_boxes[j] = dets_j[keep, :]
+    if max_detections_per_img > 0:
+        image_scores = np.hstack([cls_boxes[j][:, -1] for j in range(1, num_classes)])
+        if len(image_scores) > max_detections_per_img:
+            image_thresh = np.sort(image_scores)[-max_detections_per_img]
+            for j in range(1, num_classes):
+                k = np.where(cls_boxes[j][:, -1] >= image_thresh)[0]
+                cls_boxes[j] = cls_boxes[j][k, :]
+    im_results = np.vstack([cls_boxes[j] for j in range(1, num_classes)])
+    return im_results[:, -1], im_results[:, :-1], cls_boxes
+
+
+def postprocess_output(rois, scaling_factor, im_size, class_scores, bbox_deltas, bbox_reg_weights=(10.0, 10.0, 5.0, 5.0)):
+    """result_utils.py:76-94.  rois torch [R,4]; scaling_factor torch/float; im_size (h,w)."""
+    sf = scaling_factor if torch.is_tensor(scaling_factor) else torch.tensor(float(scaling_factor))
+    boxes = rois.div(sf).squeeze(0).numpy()
+    deltas = bbox_deltas.numpy() if torch.is_tensor(bbox_deltas) else bbox_deltas
+    im = np.asarray(im_size.numpy() if torch.is_tensor(im_size) else im_size).squeeze()
+    pred = clip_tiled_boxes(bbox_transform(boxes, deltas, bbox_reg_weights), im)
+    sc = class_scores.numpy() if torch.is_tensor(class_scores) else class_scores
+    return box_results_with_nms_and_limit(sc, pred)
