@@ -1,0 +1,177 @@
+// detectorch_b200 -- C-ABI entry points for the stand-alone operators (include/detectorch_b200.h).
+#include "../../include/detectorch_b200.h"
+#include "conv_host.cuh"
+#include "roi_align.cuh"
+#include "sort_nms.cuh"
+
+using namespace dt;
+
+extern "C" const char* dt_version(void) { return "detectorch_b200 0.1 (sm_100a)"; }
+
+// ================================================================================== RoIAlign
+extern "C" int dt_roi_align_forward_nchw(const float* features, const float* rois, int64_t num_rois, int roi_cols, int channels,
+                                         int height, int width, int pooled_height, int pooled_width, float spatial_scale,
+                                         int sampling_ratio, float* out, dt_stream_t stream) {
+    if (num_rois <= 0) return 1;
+    if (roi_cols != 4 && roi_cols != 5) {
+        fprintf(stderr, "[detectorch_b200] roi_align: rois must have 4 or 5 columns\n");
+        return 0;
+    }
+    const int grid = (int)(num_rois < (int64_t)kNumSMs * 64 ? num_rois : (int64_t)kNumSMs * 64);
+    roi_align_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(features, rois, (long long)num_rois, roi_cols, channels, height, width,
+                                                                  pooled_height, pooled_width, spatial_scale, sampling_ratio, out);
+    DT_CHECK_CUDA(cudaGetLastError());
+    return 1;
+}
+
+extern "C" int launch_roi_align_forward_cuda(const int outputElements, const float* bottom_data, const float* bottom_rois,
+                                             const float spatial_scale, const int channels, const int height, const int width,
+                                             const int pooled_height, const int pooled_width, const int sampling_ratio,
+                                             float* top_data, dt_stream_t stream) {
+    const int per_roi = channels * pooled_height * pooled_width;
+    if (per_roi <= 0) return 1;
+    return dt_roi_align_forward_nchw(bottom_data, bottom_rois, outputElements / per_roi, 5, channels, height, width, pooled_height,
+                                     pooled_width, spatial_scale, sampling_ratio, top_data, stream);
+}
+
+extern "C" int dt_roi_align_forward_nhwc(const float* const* feats, const int* heights, const int* widths, const float* scales,
+                                         int num_levels, const float* rois, const int* level, const int* num_rois_dev, int max_rois,
+                                         int channels, int pooled_height, int pooled_width, int sampling_ratio, float* out,
+                                         dt_stream_t stream) {
+    if (max_rois <= 0) return 1;
+    if (num_levels < 1 || num_levels > 5 || (channels & 3)) {
+        fprintf(stderr, "[detectorch_b200] roi_align_nhwc: 1..5 levels and C %% 4 == 0 required\n");
+        return 0;
+    }
+    RoiLevels lv;
+    lv.num_levels = num_levels;
+    for (int i = 0; i < num_levels; ++i) { lv.feat[i] = feats[i]; lv.H[i] = heights[i]; lv.W[i] = widths[i]; lv.scale[i] = scales[i]; }
+    const int grid = max_rois < kNumSMs * 64 ? max_rois : kNumSMs * 64;
+    roi_align_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(lv, rois, level, num_rois_dev, max_rois, channels, pooled_height,
+                                                                  pooled_width, sampling_ratio, out);
+    DT_CHECK_CUDA(cudaGetLastError());
+    return 1;
+}
+
+// ================================================================================== NMS (single set, boxes.nms contract)
+namespace {
+struct NmsWs {
+    uint32_t *k0, *k1;
+    int *v0, *v1;
+    float4* sorted;
+    unsigned long long* removed;
+    int* flags;
+};
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline NmsWs carve_nms_ws(void* ws, int64_t n) {
+    NmsWs w;
+    uint8_t* p = (uint8_t*)ws;
+    const size_t n4 = align_up((size_t)n * 4, 256);
+    w.k0 = (uint32_t*)p; p += n4;
+    w.k1 = (uint32_t*)p; p += n4;
+    w.v0 = (int*)p; p += n4;
+    w.v1 = (int*)p; p += n4;
+    w.flags = (int*)p; p += n4;
+    w.sorted = (float4*)p; p += align_up((size_t)n * 16, 256);
+    w.removed = (unsigned long long*)p;
+    return w;
+}
+
+__global__ void __launch_bounds__(1024) nms_single_kernel(const float* __restrict__ dets, int n, float thresh, NmsWs w,
+                                                         long long* __restrict__ keep_out, int* __restrict__ num_keep) {
+    __shared__ uint32_t hist[32 * 256];
+    __shared__ NmsSmem nsm;
+    __shared__ int scan_warp[32];
+    __shared__ int running;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        w.k0[i] = float_desc_key(dets[(size_t)i * 5 + 4]);
+        w.v0[i] = i;
+        w.flags[i] = 0;
+    }
+    __syncthreads();
+    block_radix_sort_asc_u32(w.k0, w.v0, w.k1, w.v1, n, hist);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float* d = dets + (size_t)w.v0[i] * 5;
+        w.sorted[i] = make_float4(d[0], d[1], d[2], d[3]);
+    }
+    __syncthreads();
+    block_nms_sorted(w.sorted, n, thresh, 0, w.removed, &nsm);
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (!((w.removed[i >> 6] >> (i & 63)) & 1ull)) w.flags[w.v0[i]] = 1;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    // ordered compaction of the flags -> ascending original indices
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int f = (i < n) ? w.flags[i] : 0;
+        const unsigned b = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) scan_warp[warp] = __popc(b);
+        __syncthreads();
+        if (warp == 0) {
+            int v = scan_warp[lane], inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+            scan_warp[lane] = inc - v;
+            if (lane == 31) nsm.kcount = inc;   // block total (reuse a scratch int)
+        }
+        __syncthreads();
+        if (f) keep_out[running + scan_warp[warp] + __popc(b & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) running += nsm.kcount;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *num_keep = running;
+}
+}  // namespace
+
+extern "C" int64_t dt_nms_workspace_bytes(int64_t n) {
+    if (n < 1) n = 1;
+    return (int64_t)(5 * align_up((size_t)n * 4, 256) + align_up((size_t)n * 16, 256) + align_up(((size_t)n + 63) / 64 * 8, 256));
+}
+
+extern "C" int dt_nms(const float* dets, int n, float thresh, int64_t* keep_out, int* num_keep_out, void* workspace, dt_stream_t stream) {
+    if (n <= 0) {
+        DT_CHECK_CUDA(cudaMemsetAsync(num_keep_out, 0, sizeof(int), (cudaStream_t)stream));
+        return 1;
+    }
+    NmsWs w = carve_nms_ws(workspace, n);
+    nms_single_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(dets, n, thresh, w, (long long*)keep_out, num_keep_out);
+    DT_CHECK_CUDA(cudaGetLastError());
+    return 1;
+}
+
+// ================================================================================== conv / GEMM
+namespace {
+__global__ void tf32_residual_kernel(const float* __restrict__ w, float* __restrict__ lo, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = w[i];
+        lo[i] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    }
+}
+}  // namespace
+
+extern "C" int dt_tf32_residual(const float* w, float* w_lo, int64_t n, dt_stream_t stream) {
+    if (n <= 0) return 1;
+    const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+    tf32_residual_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, w_lo, (long long)n);
+    DT_CHECK_CUDA(cudaGetLastError());
+    return 1;
+}
+
+extern "C" int dt_conv2d_nhwc(const float* x, int N, int H, int W, int Cin, int x_pix_stride, const float* w, const float* w_lo, int Cout,
+                              int kh, int kw, int pad, int stride, const float* scale, const float* shift, const float* residual,
+                              int res_mode, const float* up_src, int up_h, int up_w, int relu, int sigmoid_ch, int passes,
+                              int force_block_n, float* y, int y_pix_stride, dt_stream_t stream) {
+    ConvSpec s;
+    memset(&s, 0, sizeof(s));
+    s.x = x; s.N = N; s.H = H; s.W = W; s.Cin = Cin; s.x_pix_stride = x_pix_stride;
+    s.w_hi = w; s.w_lo = w_lo; s.Cout = Cout; s.kh = kh; s.kw = kw; s.pad = pad; s.stride = stride;
+    s.scale = scale; s.shift = shift; s.y = y; s.y_pix_stride = y_pix_stride;
+    s.residual = residual; s.res_pix_stride = Cout; s.up_src = up_src; s.up_h = up_h; s.up_w = up_w;
+    s.res_mode = res_mode; s.relu = relu; s.sigmoid_ch = sigmoid_ch; s.passes = passes; s.force_block_n = force_block_n;
+    ConvLayer L;
+    if (!conv_build(s, &L)) return 0;
+    DT_CHECK_CUDA(conv_launch(L, (cudaStream_t)stream));
+    return 1;
+}

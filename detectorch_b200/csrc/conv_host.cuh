@@ -1,0 +1,185 @@
+// detectorch_b200 -- host side of the tcgen05 conv/GEMM engine: TMA descriptor construction,
+// tile-geometry selection and launch.  No torch types; raw device pointers only.
+#pragma once
+#include <cudaTypedefs.h>
+#include <string.h>
+
+#include "conv_tcgen05.cuh"
+
+namespace dt {
+
+// cuTensorMapEncodeTiled is a driver entry point; fetch it through the runtime so that the
+// library links against cudart only (libcuda is resolved by the driver at load time).
+inline PFN_cuTensorMapEncodeTiled_v12000 get_tmap_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) {
+            fprintf(stderr, "[detectorch_b200] cuTensorMapEncodeTiled unavailable (%s)\n", cudaGetErrorString(e));
+            return nullptr;
+        }
+        fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    }
+    return fn;
+}
+
+// 4D fp32 tensor map {d0 (contiguous), d1, d2, d3} with byte strides s1,s2,s3, SWIZZLE_128B
+inline bool make_tmap_4d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint64_t s1,
+                         uint64_t s2, uint64_t s3, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3, uint32_t e1 = 1,
+                         uint32_t e2 = 1) {
+    auto fn = get_tmap_encode();
+    if (!fn) return false;
+    cuuint64_t dims[4] = {d0, d1, d2, d3};
+    cuuint64_t strides[3] = {s1, s2, s3};
+    cuuint32_t box[4] = {b0, b1, b2, b3};
+    cuuint32_t estr[4] = {1, e1, e2, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr,
+                "[detectorch_b200] cuTensorMapEncodeTiled(4d) failed: %d dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) "
+                "box=(%u,%u,%u,%u) estr=(%u,%u)\n",
+                (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)d3,
+                (unsigned long long)s1, (unsigned long long)s2, (unsigned long long)s3, b0, b1, b2, b3, e1, e2);
+        return false;
+    }
+    return true;
+}
+
+inline bool make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t s1, uint32_t b0, uint32_t b1) {
+    auto fn = get_tmap_encode();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {d0, d1};
+    cuuint64_t strides[1] = {s1};
+    cuuint32_t box[2] = {b0, b1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "[detectorch_b200] cuTensorMapEncodeTiled(2d) failed: %d dims=(%llu,%llu) stride=%llu box=(%u,%u)\n", (int)r,
+                (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)s1, b0, b1);
+        return false;
+    }
+    return true;
+}
+
+// A conv layer instance: everything needed to (re)launch it.  Built once per (layer, shape).
+struct ConvLayer {
+    ConvParams p;
+    int block_n;
+    dim3 grid;
+    bool valid = false;
+};
+
+// Logical description of one convolution over NHWC fp32 tensors.
+struct ConvSpec {
+    const float* x; int N, H, W, Cin;          // input  [N,H,W,Cin], Cin % 32 == 0
+    int x_pix_stride;                          // floats between consecutive pixels of x (>= Cin; lets x be a channel slice)
+    const float* w_hi; const float* w_lo;      // [Cout_rows][kh*kw*Cin] K-major
+    int Cout;                                  // output channels, multiple of 4
+    int kh, kw, pad, stride;
+    const float* scale; const float* shift;    // [Cout]
+    float* y; int y_pix_stride;                // output [N,Ho,Wo,*], y_pix_stride floats between pixels (>= Cout)
+    // optional output remap (transposed conv): pixel (n,h,w) is written at y + ((n*Hy + h*ys + yo)*Wy + w*ys + xo)*y_pix_stride
+    int out_h, out_w, out_step, out_y0, out_x0;   // out_step==0 -> plain [N,Ho,Wo]
+    const float* residual; int res_pix_stride;    // RES_TILE: same geometry as the (plain) output
+    const float* up_src; int up_h, up_w;          // RES_UPSAMPLE2X
+    int res_mode, relu, sigmoid_ch, passes;
+    int force_block_n;                            // 0 = auto
+};
+
+inline void choose_box(int Wo, int Ho, int N, int max_w, int* wbox, int* hbox, int* nbox) {
+    long best_tiles = -1;
+    int bw = 1, bh = 1, bn = 1;
+    for (int w = 1; w <= Wo && w <= 128 && w <= max_w; ++w) {
+        for (int h = 1; h <= Ho && w * h <= 128; ++h) {
+            int n = 128 / (w * h);
+            if (n > N) n = N;
+            if (n < 1) n = 1;
+            long tiles = (long)ceil_div(Wo, w) * ceil_div(Ho, h) * ceil_div(N, n);
+            if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && w > bw)) {
+                best_tiles = tiles; bw = w; bh = h; bn = n;
+            }
+        }
+    }
+    *wbox = bw; *hbox = bh; *nbox = bn;
+}
+
+inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
+    memset(&L->p, 0, sizeof(ConvParams));
+    ConvParams& p = L->p;
+    if (s.Cin % 32 != 0 || s.Cout % 4 != 0) {
+        fprintf(stderr, "[detectorch_b200] conv_build: Cin must be a multiple of 32 and Cout of 4 (got %d, %d)\n", s.Cin, s.Cout);
+        return false;
+    }
+    const int Ho = (s.H + 2 * s.pad - s.kh) / s.stride + 1;
+    const int Wo = (s.W + 2 * s.pad - s.kw) / s.stride + 1;
+    int wbox, hbox, nbox;
+    choose_box(Wo, Ho, s.N, 256 / s.stride, &wbox, &hbox, &nbox);
+    int bn = s.force_block_n;
+    if (bn == 0) bn = s.Cout > 128 ? 256 : (s.Cout > 64 ? 128 : 64);
+    L->block_n = bn;
+    const int K = s.kh * s.kw * s.Cin;
+    const uint64_t xs = (uint64_t)s.x_pix_stride * 4;
+    if (!make_tmap_4d(&p.tm_a, s.x, s.Cin, s.W, s.H, s.N, xs, xs * s.W, xs * s.W * s.H, 32, wbox * s.stride, hbox * s.stride, nbox,
+                      s.stride, s.stride))
+        return false;
+    if (!make_tmap_2d(&p.tm_bhi, s.w_hi, K, s.Cout, (uint64_t)K * 4, 32, bn)) return false;
+    if (!make_tmap_2d(&p.tm_blo, s.w_lo ? s.w_lo : s.w_hi, K, s.Cout, (uint64_t)K * 4, 32, bn)) return false;
+    const uint64_t ys = (uint64_t)s.y_pix_stride * 4;
+    if (s.out_step == 0) {
+        if (!make_tmap_4d(&p.tm_d, s.y, s.Cout, Wo, Ho, s.N, ys, ys * Wo, ys * Wo * Ho, 32, wbox, hbox, nbox)) return false;
+    } else {
+        // strided scatter view: logical (w,h) -> physical (w*step + x0, h*step + y0) of an [N,out_h,out_w] map
+        const float* base = s.y + ((size_t)s.out_y0 * s.out_w + s.out_x0) * s.y_pix_stride;
+        if (!make_tmap_4d(&p.tm_d, base, s.Cout, Wo, Ho, s.N, ys * s.out_step, ys * s.out_w * s.out_step, ys * s.out_w * s.out_h, 32,
+                          wbox, hbox, nbox))
+            return false;
+    }
+    if (s.res_mode == RES_TILE) {
+        const uint64_t rs = (uint64_t)s.res_pix_stride * 4;
+        if (!make_tmap_4d(&p.tm_r, s.residual, s.Cout, Wo, Ho, s.N, rs, rs * Wo, rs * Wo * Ho, 32, wbox, hbox, nbox)) return false;
+    }
+    p.scale = s.scale; p.shift = s.shift;
+    p.up_src = s.up_src; p.up_h = s.up_h; p.up_w = s.up_w;
+    p.cin_blocks = s.Cin / 32;
+    p.kh = s.kh; p.kw = s.kw; p.pad = s.pad; p.stride = s.stride;
+    p.tiles_w = ceil_div(Wo, wbox); p.tiles_h = ceil_div(Ho, hbox); p.tiles_n = ceil_div(s.N, nbox);
+    p.wbox = wbox; p.hbox = hbox; p.nbox = nbox;
+    p.wo = Wo; p.ho = Ho; p.nimg = s.N;
+    p.cout = s.Cout;
+    p.a_tile_bytes = wbox * hbox * nbox * 128;
+    p.relu = s.relu; p.sigmoid_ch = s.sigmoid_ch; p.res_mode = s.res_mode;
+    p.passes = s.passes == 1 ? 1 : 3;
+    L->grid = dim3((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n), (unsigned)ceil_div(s.Cout, bn), 1);
+    L->valid = true;
+    return true;
+}
+
+template <int BN>
+inline cudaError_t conv_launch_bn(const ConvLayer& L, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN>::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    conv_tcgen05_kernel<BN><<<L.grid, ConvCfg<BN>::THREADS, ConvCfg<BN>::SMEM_BYTES, stream>>>(L.p);
+    return cudaGetLastError();
+}
+
+inline cudaError_t conv_launch(const ConvLayer& L, cudaStream_t stream) {
+    if (!L.valid) return cudaErrorInvalidValue;
+    switch (L.block_n) {
+        case 64: return conv_launch_bn<64>(L, stream);
+        case 128: return conv_launch_bn<128>(L, stream);
+        case 256: return conv_launch_bn<256>(L, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace dt

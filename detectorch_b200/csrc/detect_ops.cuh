@@ -1,0 +1,570 @@
+// detectorch_b200 -- the non-GEMM device stages of the detector, all on-device and sync-free:
+//   stem im2col, maxpool, P6 subsample                      (torchvision trunk glue, detector.py:183,250)
+//   rpn_proposals_kernel   top-k + decode + clip + filter + NMS(0.7)   generate_proposals.py:31-122
+//   collect_kernel         merge levels, top-N, FPN level map           collect_and_distribute...py:84-128,
+//                                                                       multilevel_rois.py:41-53
+//   softmax_split_kernel   class softmax + split cls/bbox               detector.py:277-284
+//   det_class_kernel / det_limit_kernel  decode, clip, score>0.05, per-class NMS(0.5), top-100
+//                                                                       result_utils.py:76-168, boxes.py:150-208
+//   mask_rois_kernel       detections -> scaled RoIs + FPN level        eval_mask_FPN.ipynb cell 10, multilevel_rois.py:19-39
+// The reference runs all of these on the host with numpy/Cython between device syncs.
+#pragma once
+#include "common.cuh"
+#include "sort_nms.cuh"
+
+namespace dt {
+
+static constexpr float kBBoxXformClip = 4.135166556742356f;   // log(1000/16), boxes.py:73
+
+// ---------------------------------------------------------------------------------- stem im2col
+// image NCHW [B,3,H,W] -> col [B*Ho*Wo, 160], k = c*49 + ky*7 + kx (torch weight order), k >= 147 zero.
+// 7x7 stride 2 pad 3 (torchvision resnet conv1).
+static __global__ void stem_im2col_kernel(const float* __restrict__ img, int B, int H, int W, int Ho, int Wo, float* __restrict__ col) {
+    const long long total = (long long)B * Ho * Wo * 40;   // float4 granules
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k4 = (int)(i % 40);
+        long long m = i / 40;
+        const int wo = (int)(m % Wo); m /= Wo;
+        const int ho = (int)(m % Ho);
+        const int b = (int)(m / Ho);
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k4 * 4 + j;
+            float x = 0.f;
+            if (k < 147) {
+                const int c = k / 49, r = k - c * 49, ky = r / 7, kx = r - ky * 7;
+                const int y = ho * 2 - 3 + ky, xx = wo * 2 - 3 + kx;
+                if (y >= 0 && y < H && xx >= 0 && xx < W) x = __ldg(img + (((size_t)b * 3 + c) * H + y) * W + xx);
+            }
+            v[j] = x;
+        }
+        reinterpret_cast<float4*>(col)[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// NHWC 3x3 stride-2 pad-1 max pool (torchvision maxpool)
+static __global__ void maxpool3x3s2_nhwc_kernel(const float* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo, float* __restrict__ y) {
+    const int C4 = C >> 2;
+    const long long total = (long long)B * Ho * Wo * C4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        long long m = i / C4;
+        const int wo = (int)(m % Wo); m /= Wo;
+        const int ho = (int)(m % Ho);
+        const int b = (int)(m / Ho);
+        float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        for (int dy = 0; dy < 3; ++dy) {
+            const int yy = ho * 2 - 1 + dy;
+            if (yy < 0 || yy >= H) continue;
+            for (int dx = 0; dx < 3; ++dx) {
+                const int xx = wo * 2 - 1 + dx;
+                if (xx < 0 || xx >= W) continue;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + yy) * W + xx) * C) + c4);
+                best.x = fmaxf(best.x, v.x); best.y = fmaxf(best.y, v.y); best.z = fmaxf(best.z, v.z); best.w = fmaxf(best.w, v.w);
+            }
+        }
+        reinterpret_cast<float4*>(y)[i] = best;
+    }
+}
+
+// P6 = max_pool2d(P5, kernel 1, stride 2) == stride-2 subsample (detector.py:250)
+static __global__ void subsample2_nhwc_kernel(const float* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo, float* __restrict__ y) {
+    const int C4 = C >> 2;
+    const long long total = (long long)B * Ho * Wo * C4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        long long m = i / C4;
+        const int wo = (int)(m % Wo); m /= Wo;
+        const int ho = (int)(m % Ho);
+        const int b = (int)(m / Ho);
+        reinterpret_cast<float4*>(y)[i] = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + ho * 2) * W + wo * 2) * C) + c4);
+    }
+}
+
+// NHWC [M, Cs] (first C channels) -> NCHW [B, C, HW]   (public-layout views of internal maps)
+static __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int B, int HW, int Cs, int C, float* __restrict__ y) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int p = p0 + r, c = c0 + threadIdx.x;
+        tile[r][threadIdx.x] = (p < HW && c < C) ? x[((size_t)b * HW + p) * Cs + c] : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int c = c0 + r, p = p0 + threadIdx.x;
+        if (c < C && p < HW) y[((size_t)b * C + c) * HW + p] = tile[threadIdx.x][r];
+    }
+}
+
+// NCHW [B,C,HW] -> NHWC [B,HW,C]
+static __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int B, int HW, int C, float* __restrict__ y) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int c = c0 + r, p = p0 + threadIdx.x;
+        tile[r][threadIdx.x] = (p < HW && c < C) ? x[((size_t)b * C + c) * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int p = p0 + r, c = c0 + threadIdx.x;
+        if (c < C && p < HW) y[((size_t)b * HW + p) * C + c] = tile[threadIdx.x][r];
+    }
+}
+
+// ---------------------------------------------------------------------------------- box decode helpers
+// generate_proposals.py:165-214 / boxes.py:168-208: separate mul and add (torch / numpy evaluate op by op)
+__device__ __forceinline__ float4 decode_box(float4 box, float dx, float dy, float dw, float dh) {
+    const float w = __fadd_rn(__fsub_rn(box.z, box.x), 1.0f);
+    const float h = __fadd_rn(__fsub_rn(box.w, box.y), 1.0f);
+    const float cx = __fadd_rn(box.x, __fmul_rn(0.5f, w));
+    const float cy = __fadd_rn(box.y, __fmul_rn(0.5f, h));
+    dw = fminf(dw, kBBoxXformClip);
+    dh = fminf(dh, kBBoxXformClip);
+    const float pcx = __fadd_rn(__fmul_rn(dx, w), cx);
+    const float pcy = __fadd_rn(__fmul_rn(dy, h), cy);
+    const float pw = __fmul_rn(expf(dw), w);
+    const float ph = __fmul_rn(expf(dh), h);
+    float4 o;
+    o.x = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
+    o.y = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+    o.z = __fsub_rn(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), 1.f);
+    o.w = __fsub_rn(__fadd_rn(pcy, __fmul_rn(0.5f, ph)), 1.f);
+    return o;
+}
+__device__ __forceinline__ float4 clip_box(float4 b, float wmax, float hmax) {   // wmax = W-1, hmax = H-1
+    b.x = fmaxf(fminf(b.x, wmax), 0.f); b.y = fmaxf(fminf(b.y, hmax), 0.f);
+    b.z = fmaxf(fminf(b.z, wmax), 0.f); b.w = fmaxf(fminf(b.w, hmax), 0.f);
+    return b;
+}
+
+// block-wide ordered compaction helper: returns the exclusive rank of `flag` among threads of this block
+// sweep (all threads must call); *total receives the block total.  scratch: 33 ints of shared memory.
+__device__ __forceinline__ int block_rank(bool flag, int* scratch, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const unsigned b = __ballot_sync(0xffffffffu, flag);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = __popc(b);
+    __syncthreads();
+    if (warp == 0) {
+        int v = lane < nw ? scratch[lane] : 0, inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+        scratch[lane] = inc - v;
+        if (lane == 31) scratch[32] = inc;
+    }
+    __syncthreads();
+    *total = scratch[32];
+    return scratch[warp] + __popc(b & ((1u << lane) - 1u));
+}
+
+// ---------------------------------------------------------------------------------- RPN proposals
+struct RpnLevel {
+    const float* rpn_out;    // NHWC [B,H,W,ch_stride]: ch [0,A) = objectness prob, [A+4a, A+4a+4) = deltas of anchor a
+    int H, W, A, ch_stride;
+    float stride;            // 1/spatial_scale
+    float anchors[15 * 4];   // base anchors (x1,y1,x2,y2), generate_anchors.py
+    long long ws_off;        // offset (in elements) of this level's per-image sort workspace
+    int n;                   // H*W*A
+};
+struct RpnParams {
+    RpnLevel lv[5];
+    int num_levels, B;
+    int pre_nms, post_nms;
+    float nms_thresh, min_size, scaling_factor;
+    float im_h, im_w;
+    long long ws_per_image;  // elements of sort workspace per image (sum over levels)
+    uint32_t *k0, *k1;       // [B * ws_per_image]
+    int *v0, *v1;
+    float4* cand;            // [B * L * pre_nms] decoded candidates (score-sorted)
+    float* cand_score;
+    float* out_props;        // [B, L, post_nms, 4]
+    float* out_scores;       // [B, L, post_nms]
+    int* out_counts;         // [B, L]
+    // optional teacher-forcing taps (may be null)
+    int* dbg_order;          // [B, L, pre_nms] flat anchor index of the sorted top-k
+};
+
+// grid (L, B), 1024 threads
+static __global__ void __launch_bounds__(1024) rpn_proposals_kernel(const __grid_constant__ RpnParams P) {
+    __shared__ uint32_t hist[32 * 256];
+    __shared__ NmsSmem nsm;
+    __shared__ unsigned long long removed[128];   // up to 8192 candidates
+    __shared__ int scratch[33];
+    const int l = blockIdx.x, b = blockIdx.y;
+    const RpnLevel& lv = P.lv[l];
+    const int n = lv.n;
+    uint32_t* k0 = P.k0 + (size_t)b * P.ws_per_image + lv.ws_off;
+    uint32_t* k1 = P.k1 + (size_t)b * P.ws_per_image + lv.ws_off;
+    int* v0 = P.v0 + (size_t)b * P.ws_per_image + lv.ws_off;
+    int* v1 = P.v1 + (size_t)b * P.ws_per_image + lv.ws_off;
+    const float* base = lv.rpn_out + (size_t)b * lv.H * lv.W * lv.ch_stride;
+    // 1. keys in (H,W,A) order (generate_proposals.py:64,72)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int a = i % lv.A, cell = i / lv.A;
+        k0[i] = float_desc_key(base[(size_t)cell * lv.ch_stride + a]);
+        v0[i] = i;
+    }
+    __syncthreads();
+    // 2. descending sort by score (:77-86)
+    block_radix_sort_asc_u32(k0, v0, k1, v1, n, hist);
+    const int K = (P.pre_nms <= 0 || P.pre_nms >= n) ? n : P.pre_nms;
+    // 3. decode + clip + filter on the top K (:96-112), order preserved
+    float4* cand = P.cand + ((size_t)b * P.num_levels + l) * P.pre_nms;
+    float* cscore = P.cand_score + ((size_t)b * P.num_levels + l) * P.pre_nms;
+    int nc = 0;
+    const float min_size = P.min_size * P.scaling_factor;
+    for (int base_i = 0; base_i < K; base_i += blockDim.x) {
+        const int i = base_i + threadIdx.x;
+        bool keep = false;
+        float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+        float sc = 0.f;
+        if (i < K) {
+            const int idx = v0[i];
+            if (P.dbg_order) P.dbg_order[((size_t)b * P.num_levels + l) * P.pre_nms + i] = idx;
+            const int a = idx % lv.A, cell = idx / lv.A;
+            const int x = cell % lv.W, y = cell / lv.W;
+            const float sx = (float)x * lv.stride, sy = (float)y * lv.stride;
+            const float4 anc = make_float4(lv.anchors[a * 4 + 0] + sx, lv.anchors[a * 4 + 1] + sy, lv.anchors[a * 4 + 2] + sx,
+                                           lv.anchors[a * 4 + 3] + sy);
+            const float* d = base + (size_t)cell * lv.ch_stride + lv.A + a * 4;
+            sc = base[(size_t)cell * lv.ch_stride + a];
+            box = clip_box(decode_box(anc, d[0], d[1], d[2], d[3]), P.im_w - 1.f, P.im_h - 1.f);
+            // filter_boxes (:151-163)
+            const float ws = __fadd_rn(__fsub_rn(box.z, box.x), 1.f), hs = __fadd_rn(__fsub_rn(box.w, box.y), 1.f);
+            const float xc = __fadd_rn(box.x, __fdiv_rn(ws, 2.f)), yc = __fadd_rn(box.y, __fdiv_rn(hs, 2.f));
+            keep = (ws >= min_size) && (hs >= min_size) && (xc < P.im_w) && (yc < P.im_h);
+        }
+        int tot;
+        const int r = block_rank(keep, scratch, &tot);
+        if (keep) { cand[nc + r] = box; cscore[nc + r] = sc; }
+        nc += tot;
+    }
+    __syncthreads();
+    // 4. NMS (:114-120); candidates are already in descending-score order
+    float* op = P.out_props + ((size_t)b * P.num_levels + l) * P.post_nms * 4;
+    float* os = P.out_scores + ((size_t)b * P.num_levels + l) * P.post_nms;
+    int nout = 0;
+    if (P.nms_thresh > 0.f) {
+        block_nms_sorted(cand, nc, P.nms_thresh, P.post_nms, removed, &nsm);
+        for (int base_i = 0; base_i < nc; base_i += blockDim.x) {
+            const int i = base_i + threadIdx.x;
+            const bool keep = (i < nc) && !((removed[i >> 6] >> (i & 63)) & 1ull);
+            int tot;
+            const int r = block_rank(keep, scratch, &tot);
+            const int pos = nout + r;
+            if (keep && (P.post_nms <= 0 || pos < P.post_nms)) {
+                const float4 bx = cand[i];
+                op[pos * 4 + 0] = bx.x; op[pos * 4 + 1] = bx.y; op[pos * 4 + 2] = bx.z; op[pos * 4 + 3] = bx.w;
+                os[pos] = cscore[i];
+            }
+            nout += tot;
+        }
+        if (P.post_nms > 0 && nout > P.post_nms) nout = P.post_nms;
+    } else {
+        nout = min(nc, P.post_nms);
+        for (int i = threadIdx.x; i < nout; i += blockDim.x) {
+            const float4 bx = cand[i];
+            op[i * 4 + 0] = bx.x; op[i * 4 + 1] = bx.y; op[i * 4 + 2] = bx.z; op[i * 4 + 3] = bx.w;
+            os[i] = cscore[i];
+        }
+    }
+    if (threadIdx.x == 0) P.out_counts[b * P.num_levels + l] = nout;
+}
+
+// ---------------------------------------------------------------------------------- collect + distribute
+// FPN level heuristic, multilevel_rois.py:41-53 (fp32 numpy arithmetic)
+__device__ __forceinline__ int fpn_level(float4 box, int k_min, int k_max) {
+    const float area = box_area_p1(box);
+    const float s = sqrtf(area);
+    float lvl = floorf(__fadd_rn(4.f, log2f(__fadd_rn(__fdiv_rn(s, 224.f), 1e-6f))));
+    lvl = fminf(fmaxf(lvl, (float)k_min), (float)k_max);
+    return (int)lvl;
+}
+
+struct CollectParams {
+    const float* props;      // [B, L, post_nms, 4]
+    const float* scores;     // [B, L, post_nms]
+    const int* counts;       // [B, L]
+    int B, L, post_nms, top_n;
+    int k_min, k_max;
+    uint32_t *k0, *k1;       // [B, L*post_nms]
+    int *v0, *v1;
+    float* rois;             // [B, top_n, 5] (batch idx, x1,y1,x2,y2); rows >= count are zero
+    int* levels;             // [B, top_n] level index (lvl - k_min)
+    int* roi_counts;         // [B]
+};
+
+// grid B, 1024 threads
+static __global__ void __launch_bounds__(1024) collect_kernel(const __grid_constant__ CollectParams P) {
+    __shared__ uint32_t hist[32 * 256];
+    __shared__ int seg_off[8];
+    const int b = blockIdx.x;
+    const int cap = P.L * P.post_nms;
+    uint32_t* k0 = P.k0 + (size_t)b * cap; uint32_t* k1 = P.k1 + (size_t)b * cap;
+    int* v0 = P.v0 + (size_t)b * cap; int* v1 = P.v1 + (size_t)b * cap;
+    if (threadIdx.x == 0) {
+        int o = 0;
+        for (int l = 0; l < P.L; ++l) { seg_off[l] = o; o += P.counts[b * P.L + l]; }
+        seg_off[P.L] = o;
+    }
+    __syncthreads();
+    const int n = seg_off[P.L];
+    // concatenation in level order (collect...py:98-100); value = l*post_nms + i
+    for (int l = 0; l < P.L; ++l) {
+        const int c = seg_off[l + 1] - seg_off[l];
+        for (int i = threadIdx.x; i < c; i += blockDim.x) {
+            k0[seg_off[l] + i] = float_desc_key(P.scores[((size_t)b * P.L + l) * P.post_nms + i]);
+            v0[seg_off[l] + i] = l * P.post_nms + i;
+        }
+    }
+    __syncthreads();
+    block_radix_sort_asc_u32(k0, v0, k1, v1, n, hist);      // torch.sort(-scores) (:102)
+    const int m = min(n, P.top_n);
+    for (int i = threadIdx.x; i < P.top_n; i += blockDim.x) {
+        float* r = P.rois + ((size_t)b * P.top_n + i) * 5;
+        if (i < m) {
+            const float* p = P.props + ((size_t)b * cap + v0[i]) * 4;
+            const float4 box = make_float4(p[0], p[1], p[2], p[3]);
+            r[0] = (float)b; r[1] = box.x; r[2] = box.y; r[3] = box.z; r[4] = box.w;
+            P.levels[(size_t)b * P.top_n + i] = fpn_level(box, P.k_min, P.k_max) - P.k_min;
+        } else {
+            r[0] = (float)b; r[1] = r[2] = r[3] = r[4] = 0.f;
+            P.levels[(size_t)b * P.top_n + i] = 0;
+        }
+    }
+    if (threadIdx.x == 0) P.roi_counts[b] = m;
+}
+
+// ---------------------------------------------------------------------------------- box head tail
+// head [M, stride] with [0,NC) class logits and [NC, NC+4NC) box deltas -> cls_prob [M,NC] (softmax), bbox [M,4NC]
+// one warp per row
+static __global__ void softmax_split_kernel(const float* __restrict__ head, int M, int stride, int NC, int do_softmax,
+                                     float* __restrict__ cls, float* __restrict__ bbox) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float* h = head + (size_t)row * stride;
+    float mx = -INFINITY;
+    for (int c = lane; c < NC; c += 32) mx = fmaxf(mx, h[c]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int c = lane; c < NC; c += 32) sum += expf(h[c] - mx);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int c = lane; c < NC; c += 32) cls[(size_t)row * NC + c] = do_softmax ? __fdiv_rn(expf(h[c] - mx), sum) : h[c];
+    for (int c = lane; c < 4 * NC; c += 32) bbox[(size_t)row * 4 * NC + c] = h[NC + c];
+}
+
+// ---------------------------------------------------------------------------------- detection post-processing
+struct DetParams {
+    const float* rois;        // [B, R, 5] image-scale RoIs (col 0 = batch)
+    const int* roi_counts;    // [B] (null -> R)
+    const float* cls;         // [B*R, NC]
+    const float* bbox;        // [B*R, 4*NC]
+    int B, R, NC;
+    float scaling_factor, im_h, im_w;      // original image size = network size / scaling_factor
+    float wx, wy, ww, wh;                  // bbox_reg_weights (10,10,5,5)
+    float score_thresh, nms_thresh;
+    int max_dets, out_cap;                 // 100, and the padded capacity of the outputs (>= max_dets)
+    // per (image, class) scratch: kept flags over RoIs, decoded boxes
+    unsigned char* keep_flag;   // [B, NC, R]
+    float4* dec_box;            // [B, NC, R]
+    int* cls_counts;            // [B, NC]
+    // sort scratch for the limit step
+    uint32_t *k0, *k1;          // [B, NC*R]
+    int *v0, *v1;
+    // outputs, class-major then ascending RoI index (result_utils.py:165-168)
+    float* out_boxes;           // [B, out_cap, 4]
+    float* out_scores;          // [B, out_cap]
+    int* out_classes;           // [B, out_cap]
+    int* out_roi_idx;           // [B, out_cap]
+    int* out_counts;            // [B]
+};
+
+// grid (NC-1, B), 256 threads; one CTA = one (image, foreground class).  R <= 1024.
+static __global__ void __launch_bounds__(256) det_class_kernel(const __grid_constant__ DetParams P) {
+    __shared__ unsigned long long skey[1024];       // (score desc, roi idx asc) sort keys
+    __shared__ float4 sbox[1024];
+    __shared__ NmsSmem nsm;
+    __shared__ unsigned long long removed[16];
+    __shared__ int scratch[33];
+    const int j = blockIdx.x + 1, b = blockIdx.y;
+    const int R = P.roi_counts ? min(P.roi_counts[b], P.R) : P.R;
+    unsigned char* flag = P.keep_flag + ((size_t)b * P.NC + j) * P.R;
+    float4* dbox = P.dec_box + ((size_t)b * P.NC + j) * P.R;
+    // candidates: score > thresh (strict, result_utils.py:127), ascending RoI order
+    int nc = 0;
+    for (int base = 0; base < P.R; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        float sc = 0.f;
+        bool c = false;
+        if (i < R) { sc = P.cls[((size_t)b * P.R + i) * P.NC + j]; c = sc > P.score_thresh; }
+        if (i < P.R) flag[i] = 0;
+        int tot;
+        const int r = block_rank(c, scratch, &tot);
+        if (c) {
+            // ascending radix order of the 64-bit key == (score desc, idx asc)
+            skey[nc + r] = ((unsigned long long)float_desc_key(sc) << 32) | (unsigned)i;
+        }
+        nc += tot;
+    }
+    __syncthreads();
+    if (nc == 0) { if (threadIdx.x == 0) P.cls_counts[b * P.NC + j] = 0; return; }
+    // bitonic sort of nc keys padded to a power of two
+    int np2 = 1; while (np2 < nc) np2 <<= 1;
+    for (int i = nc + threadIdx.x; i < np2; i += blockDim.x) skey[i] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int s = k >> 1; s > 0; s >>= 1) {
+            for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+                const int p = i ^ s;
+                if (p > i) {
+                    const unsigned long long a = skey[i], c = skey[p];
+                    const bool up = ((i & k) == 0);
+                    if ((a > c) == up) { skey[i] = c; skey[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // decode + clip the candidates of this class (boxes.py:168-208,150-165), sorted order
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+        const int ri = (int)(skey[i] & 0xffffffffu);
+        const float* r = P.rois + ((size_t)b * P.R + ri) * 5;
+        const float4 box = make_float4(__fdiv_rn(r[1], P.scaling_factor), __fdiv_rn(r[2], P.scaling_factor),
+                                       __fdiv_rn(r[3], P.scaling_factor), __fdiv_rn(r[4], P.scaling_factor));
+        const float* d = P.bbox + ((size_t)b * P.R + ri) * 4 * P.NC + 4 * j;
+        float4 o = decode_box(box, __fdiv_rn(d[0], P.wx), __fdiv_rn(d[1], P.wy), __fdiv_rn(d[2], P.ww), __fdiv_rn(d[3], P.wh));
+        o = clip_box(o, P.im_w - 1.f, P.im_h - 1.f);
+        sbox[i] = o;
+        dbox[ri] = o;
+    }
+    __syncthreads();
+    const int kept = block_nms_sorted(sbox, nc, P.nms_thresh, 0, removed, &nsm);
+    for (int i = threadIdx.x; i < nc; i += blockDim.x)
+        if (!((removed[i >> 6] >> (i & 63)) & 1ull)) flag[(int)(skey[i] & 0xffffffffu)] = 1;
+    if (threadIdx.x == 0) P.cls_counts[b * P.NC + j] = kept;
+}
+
+// grid B, 1024 threads: limit to max_dets over all classes (result_utils.py:152-168) and emit
+static __global__ void __launch_bounds__(1024) det_limit_kernel(const __grid_constant__ DetParams P) {
+    __shared__ uint32_t hist[32 * 256];
+    __shared__ int scratch[33];
+    __shared__ float s_thresh;
+    const int b = blockIdx.x;
+    const size_t cap = (size_t)P.NC * P.R;
+    uint32_t* k0 = P.k0 + b * cap; uint32_t* k1 = P.k1 + b * cap;
+    int* v0 = P.v0 + b * cap; int* v1 = P.v1 + b * cap;
+    const unsigned char* flag = P.keep_flag + (size_t)b * P.NC * P.R;
+    // gather kept (class-major, RoI ascending)
+    int n = 0;
+    for (int base = P.R; base < (int)cap; base += blockDim.x) {     // class 0 (background) skipped
+        const int i = base + threadIdx.x;
+        const bool f = (i < (int)cap) && flag[i];
+        int tot;
+        const int r = block_rank(f, scratch, &tot);
+        if (f) {
+            const int j = i / P.R, ri = i - j * P.R;
+            k0[n + r] = float_desc_key(P.cls[((size_t)b * P.R + ri) * P.NC + j]);
+            v0[n + r] = i;
+        }
+        n += tot;
+    }
+    __syncthreads();
+    float thresh = -INFINITY;
+    if (P.max_dets > 0 && n > P.max_dets) {
+        // image_thresh = np.sort(image_scores)[-max_dets]  == max_dets-th largest
+        block_radix_sort_asc_u32(k0, v0, k1, v1, n, hist);
+        if (threadIdx.x == 0) {
+            const int i = v0[P.max_dets - 1];
+            const int j = i / P.R, ri = i - j * P.R;
+            s_thresh = P.cls[((size_t)b * P.R + ri) * P.NC + j];
+        }
+        __syncthreads();
+        thresh = s_thresh;
+    }
+    // emit in class-major / RoI-ascending order, score >= thresh (:162)
+    int nout = 0;
+    for (int base = P.R; base < (int)cap; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        bool f = false;
+        float sc = 0.f;
+        int j = 0, ri = 0;
+        if (i < (int)cap && flag[i]) {
+            j = i / P.R; ri = i - j * P.R;
+            sc = P.cls[((size_t)b * P.R + ri) * P.NC + j];
+            f = sc >= thresh;
+        }
+        int tot;
+        const int r = block_rank(f, scratch, &tot);
+        const int pos = nout + r;
+        if (f && pos < P.out_cap) {
+            const float4 bx = P.dec_box[((size_t)b * P.NC + j) * P.R + ri];
+            float* ob = P.out_boxes + ((size_t)b * P.out_cap + pos) * 4;
+            ob[0] = bx.x; ob[1] = bx.y; ob[2] = bx.z; ob[3] = bx.w;
+            P.out_scores[(size_t)b * P.out_cap + pos] = sc;
+            P.out_classes[(size_t)b * P.out_cap + pos] = j;
+            P.out_roi_idx[(size_t)b * P.out_cap + pos] = ri;
+        }
+        nout += tot;
+    }
+    for (int i = min(nout, P.out_cap) + threadIdx.x; i < P.out_cap; i += blockDim.x) {
+        float* ob = P.out_boxes + ((size_t)b * P.out_cap + i) * 4;
+        ob[0] = ob[1] = ob[2] = ob[3] = 0.f;
+        P.out_scores[(size_t)b * P.out_cap + i] = 0.f;
+        P.out_classes[(size_t)b * P.out_cap + i] = 0;
+        P.out_roi_idx[(size_t)b * P.out_cap + i] = -1;
+    }
+    if (threadIdx.x == 0) P.out_counts[b] = min(nout, P.out_cap);
+}
+
+// detections -> mask RoIs: boxes_final * scaling_factor, FPN level (eval_mask_FPN.ipynb cell 10; multilevel_rois.py:19-39)
+static __global__ void mask_rois_kernel(const float* __restrict__ boxes, const int* __restrict__ counts, int B, int cap, float scaling_factor,
+                                 int k_min, int k_max, float* __restrict__ rois5, int* __restrict__ levels) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * cap) return;
+    const int b = i / cap, d = i - b * cap;
+    float* r = rois5 + (size_t)i * 5;
+    r[0] = (float)b;
+    if (d < counts[b]) {
+        const float* s = boxes + (size_t)i * 4;
+        const float4 box = make_float4(__fmul_rn(s[0], scaling_factor), __fmul_rn(s[1], scaling_factor), __fmul_rn(s[2], scaling_factor),
+                                       __fmul_rn(s[3], scaling_factor));
+        r[1] = box.x; r[2] = box.y; r[3] = box.z; r[4] = box.w;
+        levels[i] = fpn_level(box, k_min, k_max) - k_min;
+    } else {
+        r[1] = r[2] = r[3] = r[4] = 0.f;
+        levels[i] = 0;
+    }
+}
+
+// mask logits NHWC [D, S, S, stride] -> per-detection mask of its own class [D, S, S] (+sigmoid), and optionally
+// the full public tensor [D, NC, S, S]
+static __global__ void mask_select_kernel(const float* __restrict__ logits, const int* __restrict__ classes, int D, int S, int stride, int NC,
+                                   int apply_sigmoid, float* __restrict__ sel, float* __restrict__ full) {
+    const long long total = (long long)D * S * S;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)(i / (S * S));
+        const int p = (int)(i - (long long)d * S * S);
+        const float* src = logits + ((size_t)d * S * S + p) * stride;
+        if (sel) {
+            const int c = classes ? classes[d] : 0;
+            float v = src[c];
+            if (apply_sigmoid) v = 1.f / (1.f + expf(-v));
+            sel[i] = v;
+        }
+        if (full) {
+            for (int c = 0; c < NC; ++c) {
+                float v = src[c];
+                if (apply_sigmoid) v = 1.f / (1.f + expf(-v));
+                full[((size_t)d * NC + c) * S * S + p] = v;
+            }
+        }
+    }
+}
+
+}  // namespace dt

@@ -1,0 +1,182 @@
+// detectorch_b200 -- RoIAlign forward (caffe2 semantics, no RoI rounding, RoI >= 1x1,
+// average of grid_h x grid_w bilinear samples; samples outside [-1,H]x[-1,W] contribute 0).
+// Reference: lib/cppcuda_cffi/src/cuda/roi_align_forward_cuda_kernel.cu:30-159 (GPU),
+//            lib/cppcuda_cffi/src/cpp/roi_align_cpu_loop.cpp:118-224 (CPU loop = parity oracle).
+//
+// Two layouts:
+//  * roi_align_nchw_kernel  : the reference's public layout (features NCHW, out [R,C,ph,pw]).
+//    One CTA per RoI; the separable 1-D sample tables (y taps / x taps) are built once per RoI in
+//    shared memory and shared by all channels; threads sweep the RoI's contiguous C*ph*pw output
+//    run so stores are fully coalesced.  The fp32 expression order of the reference CPU loop is
+//    reproduced with explicit _rn intrinsics (no FMA contraction) => bit-identical to the oracle.
+//  * roi_align_nhwc_kernel  : internal layout of the fused detector (features NHWC, multi-level,
+//    out [R,ph,pw,C]); every tap is one 128-bit load of 4 channels, stores are 128-bit.
+#pragma once
+#include "common.cuh"
+
+namespace dt {
+
+struct AxisTap {      // one 1-D bilinear sample along an axis
+    int lo, hi;       // cell indices
+    float wl, wh;     // weight of lo / hi cell (hy / ly in the reference's naming)
+    int valid;        // 0 -> sample is outside [-1, extent] and contributes nothing
+};
+
+// reference bilinear_interpolate() :30-80, one axis at a time (the test and the clamps are separable)
+__device__ __forceinline__ AxisTap axis_tap(float v, int extent) {
+    AxisTap t;
+    t.valid = !(v < -1.0f || v > (float)extent);
+    if (v <= 0.f) v = 0.f;
+    int lo = (int)v;
+    int hi;
+    if (lo >= extent - 1) { hi = lo = extent - 1; v = (float)lo; } else { hi = lo + 1; }
+    const float l = __fsub_rn(v, (float)lo);
+    t.lo = lo; t.hi = hi; t.wh = l; t.wl = __fsub_rn(1.f, l);
+    return t;
+}
+
+struct RoiGeom {
+    float start_w, start_h, bin_w, bin_h;
+    int grid_w, grid_h, batch;
+};
+
+__device__ __forceinline__ RoiGeom roi_geom(const float* r, int roi_cols, float scale, int ph, int pw, int sampling_ratio) {
+    RoiGeom g;
+    g.batch = 0;
+    if (roi_cols == 5) { g.batch = (int)r[0]; ++r; }
+    g.start_w = __fmul_rn(r[0], scale); g.start_h = __fmul_rn(r[1], scale);
+    const float end_w = __fmul_rn(r[2], scale), end_h = __fmul_rn(r[3], scale);
+    const float rw = fmaxf(__fsub_rn(end_w, g.start_w), 1.f), rh = fmaxf(__fsub_rn(end_h, g.start_h), 1.f);
+    g.bin_h = __fdiv_rn(rh, (float)ph); g.bin_w = __fdiv_rn(rw, (float)pw);
+    g.grid_h = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(__fdiv_rn(rh, (float)ph));
+    g.grid_w = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(__fdiv_rn(rw, (float)pw));
+    return g;
+}
+
+// sample coordinate: start + p*bin + (i + .5f)*bin/grid, evaluated left to right in fp32 (:140-147)
+__device__ __forceinline__ float sample_coord(float start, int p, float bin, int i, int grid) {
+    return __fadd_rn(__fadd_rn(start, __fmul_rn((float)p, bin)), __fdiv_rn(__fmul_rn((float)i + .5f, bin), (float)grid));
+}
+
+static constexpr int kMaxAxisSamples = 512;   // pooled * grid per axis held in smem (14 * 36 fits)
+
+// ---------------------------------------------------------------------------------- NCHW (public layout)
+static __global__ void __launch_bounds__(256) roi_align_nchw_kernel(const float* __restrict__ feat, const float* __restrict__ rois,
+                                                            long long num_rois, int roi_cols, int C, int H, int W, int PH, int PW,
+                                                            float scale, int sampling_ratio, float* __restrict__ out) {
+    __shared__ AxisTap ytab[kMaxAxisSamples];
+    __shared__ AxisTap xtab[kMaxAxisSamples];
+    for (long long n = blockIdx.x; n < num_rois; n += gridDim.x) {
+        const RoiGeom g = roi_geom(rois + n * roi_cols, roi_cols, scale, PH, PW, sampling_ratio);
+        const int ny = PH * g.grid_h, nx = PW * g.grid_w;
+        const bool tabled = (ny <= kMaxAxisSamples) && (nx <= kMaxAxisSamples);
+        __syncthreads();   // previous RoI's table no longer in use
+        if (tabled) {
+            for (int i = threadIdx.x; i < ny + nx; i += blockDim.x) {
+                if (i < ny) ytab[i] = axis_tap(sample_coord(g.start_h, i / g.grid_h, g.bin_h, i % g.grid_h, g.grid_h), H);
+                else { const int k = i - ny; xtab[k] = axis_tap(sample_coord(g.start_w, k / g.grid_w, g.bin_w, k % g.grid_w, g.grid_w), W); }
+            }
+        }
+        __syncthreads();
+        const float count = (float)(g.grid_h * g.grid_w);
+        const int per_roi = C * PH * PW;
+        const float* fb = feat + (size_t)g.batch * C * H * W;
+        float* ob = out + (size_t)n * per_roi;
+        for (int o = threadIdx.x; o < per_roi; o += blockDim.x) {
+            const int pw = o % PW;
+            const int ph = (o / PW) % PH;
+            const int c = o / (PW * PH);
+            const float* plane = fb + (size_t)c * H * W;
+            float acc = 0.f;
+            for (int iy = 0; iy < g.grid_h; ++iy) {
+                const AxisTap ty = tabled ? ytab[ph * g.grid_h + iy] : axis_tap(sample_coord(g.start_h, ph, g.bin_h, iy, g.grid_h), H);
+                const float* r0 = plane + (size_t)ty.lo * W;
+                const float* r1 = plane + (size_t)ty.hi * W;
+                for (int ix = 0; ix < g.grid_w; ++ix) {
+                    const AxisTap tx = tabled ? xtab[pw * g.grid_w + ix] : axis_tap(sample_coord(g.start_w, pw, g.bin_w, ix, g.grid_w), W);
+                    if (ty.valid && tx.valid) {
+                        // val = w1*v1 + w2*v2 + w3*v3 + w4*v4, left to right, then acc += val  (cpu_loop.cpp:207-212)
+                        const float w1 = __fmul_rn(ty.wl, tx.wl), w2 = __fmul_rn(ty.wl, tx.wh);
+                        const float w3 = __fmul_rn(ty.wh, tx.wl), w4 = __fmul_rn(ty.wh, tx.wh);
+                        float v = __fmul_rn(w1, __ldg(r0 + tx.lo));
+                        v = __fadd_rn(v, __fmul_rn(w2, __ldg(r0 + tx.hi)));
+                        v = __fadd_rn(v, __fmul_rn(w3, __ldg(r1 + tx.lo)));
+                        v = __fadd_rn(v, __fmul_rn(w4, __ldg(r1 + tx.hi)));
+                        acc = __fadd_rn(acc, v);
+                    }
+                }
+            }
+            ob[o] = __fdiv_rn(acc, count);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- NHWC multi-level (internal layout)
+struct RoiLevels {
+    const float* feat[5];   // NHWC maps, finest first
+    int H[5], W[5];
+    float scale[5];
+    int num_levels;
+};
+
+// rois [R,5] (batch,x1,y1,x2,y2); level[R] (index into lv, or nullptr -> level 0); out [R,PH,PW,C].
+// grid: one CTA per RoI (grid-stride). C % 4 == 0.
+static __global__ void __launch_bounds__(256) roi_align_nhwc_kernel(RoiLevels lv, const float* __restrict__ rois, const int* __restrict__ level,
+                                                            const int* __restrict__ num_rois_dev, int max_rois, int C, int PH, int PW,
+                                                            int sampling_ratio, float* __restrict__ out) {
+    __shared__ AxisTap ytab[kMaxAxisSamples];
+    __shared__ AxisTap xtab[kMaxAxisSamples];
+    const int num_rois = num_rois_dev ? min(*num_rois_dev, max_rois) : max_rois;
+    const int C4 = C >> 2;
+    for (int n = blockIdx.x; n < max_rois; n += gridDim.x) {
+        float4* ob = reinterpret_cast<float4*>(out + (size_t)n * PH * PW * C);
+        const int per_roi = PH * PW * C4;
+        if (n >= num_rois) {    // padded slot: defined (zero) output
+            for (int o = threadIdx.x; o < per_roi; o += blockDim.x) ob[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
+        const int l = level ? level[n] : 0;
+        const int H = lv.H[l], W = lv.W[l];
+        const RoiGeom g = roi_geom(rois + (size_t)n * 5, 5, lv.scale[l], PH, PW, sampling_ratio);
+        const int ny = PH * g.grid_h, nx = PW * g.grid_w;
+        const bool tabled = (ny <= kMaxAxisSamples) && (nx <= kMaxAxisSamples);
+        __syncthreads();
+        if (tabled) {
+            for (int i = threadIdx.x; i < ny + nx; i += blockDim.x) {
+                if (i < ny) ytab[i] = axis_tap(sample_coord(g.start_h, i / g.grid_h, g.bin_h, i % g.grid_h, g.grid_h), H);
+                else { const int k = i - ny; xtab[k] = axis_tap(sample_coord(g.start_w, k / g.grid_w, g.bin_w, k % g.grid_w, g.grid_w), W); }
+            }
+        }
+        __syncthreads();
+        const float count = (float)(g.grid_h * g.grid_w);
+        const float4* fb = reinterpret_cast<const float4*>(lv.feat[l] + (size_t)g.batch * H * W * C);
+        for (int o = threadIdx.x; o < per_roi; o += blockDim.x) {
+            const int c4 = o % C4;
+            const int bin = o / C4;
+            const int pw = bin % PW, ph = bin / PW;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int iy = 0; iy < g.grid_h; ++iy) {
+                const AxisTap ty = tabled ? ytab[ph * g.grid_h + iy] : axis_tap(sample_coord(g.start_h, ph, g.bin_h, iy, g.grid_h), H);
+                for (int ix = 0; ix < g.grid_w; ++ix) {
+                    const AxisTap tx = tabled ? xtab[pw * g.grid_w + ix] : axis_tap(sample_coord(g.start_w, pw, g.bin_w, ix, g.grid_w), W);
+                    if (ty.valid && tx.valid) {
+                        const float w1 = __fmul_rn(ty.wl, tx.wl), w2 = __fmul_rn(ty.wl, tx.wh);
+                        const float w3 = __fmul_rn(ty.wh, tx.wl), w4 = __fmul_rn(ty.wh, tx.wh);
+                        const float4 v1 = __ldg(fb + ((size_t)ty.lo * W + tx.lo) * C4 + c4);
+                        const float4 v2 = __ldg(fb + ((size_t)ty.lo * W + tx.hi) * C4 + c4);
+                        const float4 v3 = __ldg(fb + ((size_t)ty.hi * W + tx.lo) * C4 + c4);
+                        const float4 v4 = __ldg(fb + ((size_t)ty.hi * W + tx.hi) * C4 + c4);
+#define DT_TAP(f)                                                                                       \
+    acc.f = __fadd_rn(acc.f, __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1.f), __fmul_rn(w2, v2.f)), \
+                                                   __fmul_rn(w3, v3.f)), __fmul_rn(w4, v4.f)));
+                        DT_TAP(x) DT_TAP(y) DT_TAP(z) DT_TAP(w)
+#undef DT_TAP
+                    }
+                }
+            }
+            ob[o] = make_float4(__fdiv_rn(acc.x, count), __fdiv_rn(acc.y, count), __fdiv_rn(acc.z, count), __fdiv_rn(acc.w, count));
+        }
+    }
+}
+
+}  // namespace dt

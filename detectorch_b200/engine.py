@@ -1,0 +1,161 @@
+"""Python handle on the fused C++/CUDA engine (include/detectorch_b200.h, dt_engine_*).
+Torch only provides the two flat device buffers, the stream and zero-copy views of the named
+engine tensors; every kernel is launched by the C++ side."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+ARCH_BLOCKS = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3)}
+
+
+def param_table(arch="resnet50", use_mask=True, num_classes=81):
+    """{reference state_dict name: numel} the engine expects (no GPU needed)."""
+    L = _lib.lib()
+    _bind_engine_api(L)
+    cfg = EngineConfig()
+    cfg.arch_blocks = (ctypes.c_int * 4)(*ARCH_BLOCKS[arch])
+    cfg.batch, cfg.height, cfg.width = 1, 64, 64
+    cfg.pre_nms_top_n = cfg.post_nms_top_n = 1000
+    cfg.num_classes, cfg.max_dets, cfg.det_cap, cfg.use_mask = num_classes, 100, 100, int(use_mask)
+    h = L.dt_engine_create(ctypes.byref(cfg))
+    out = {}
+    buf = ctypes.create_string_buffer(256)
+    n = ctypes.c_int64()
+    for i in range(L.dt_engine_param_count(h)):
+        L.dt_engine_param_info(h, i, buf, 256, ctypes.byref(n))
+        out[buf.value.decode()] = n.value
+    L.dt_engine_destroy(h)
+    return out
+
+# stage ids (dt_engine_run)
+ST_TRUNK, ST_FPN, ST_RPN, ST_PROPOSALS, ST_COLLECT, ST_ROI_BOX, ST_BOX_HEAD, ST_DETECT, ST_MASK_ROIS, ST_MASK_ROI_FEAT, \
+    ST_MASK_HEAD, ST_MASK_OUT = range(12)
+
+
+class EngineConfig(ctypes.Structure):
+    _fields_ = [("arch_blocks", ctypes.c_int * 4), ("batch", ctypes.c_int), ("height", ctypes.c_int), ("width", ctypes.c_int),
+                ("pre_nms_top_n", ctypes.c_int), ("post_nms_top_n", ctypes.c_int), ("rpn_nms_thresh", ctypes.c_float),
+                ("rpn_min_size", ctypes.c_float), ("num_classes", ctypes.c_int), ("score_thresh", ctypes.c_float),
+                ("det_nms_thresh", ctypes.c_float), ("max_dets", ctypes.c_int), ("det_cap", ctypes.c_int),
+                ("use_mask", ctypes.c_int), ("output_prob", ctypes.c_int), ("emit_full_masks", ctypes.c_int),
+                ("passes", ctypes.c_int)]
+
+
+_DTYPES = {0: torch.float32, 1: torch.int32, 2: torch.uint8}
+
+
+def _bind_engine_api(L):
+    if getattr(L, "_engine_bound", False):
+        return
+    vp, ci, c64, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+    L.dt_engine_create.restype, L.dt_engine_create.argtypes = vp, [ctypes.POINTER(EngineConfig)]
+    L.dt_engine_destroy.restype, L.dt_engine_destroy.argtypes = None, [vp]
+    L.dt_engine_weight_bytes.restype, L.dt_engine_weight_bytes.argtypes = c64, [vp]
+    L.dt_engine_workspace_bytes.restype, L.dt_engine_workspace_bytes.argtypes = c64, [vp]
+    L.dt_engine_bind.restype, L.dt_engine_bind.argtypes = ci, [vp, vp, vp, vp]
+    L.dt_engine_load_param.restype, L.dt_engine_load_param.argtypes = ci, [vp, ctypes.c_char_p, vp, c64, vp]
+    L.dt_engine_finalize_weights.restype, L.dt_engine_finalize_weights.argtypes = ci, [vp, vp]
+    L.dt_engine_buffer.restype = ci
+    L.dt_engine_buffer.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(c64), ctypes.POINTER(ci), ctypes.POINTER(ci * 5), ctypes.POINTER(ci)]
+    L.dt_engine_num_stages.restype, L.dt_engine_num_stages.argtypes = ci, []
+    L.dt_engine_param_count.restype, L.dt_engine_param_count.argtypes = ci, [vp]
+    L.dt_engine_param_info.restype, L.dt_engine_param_info.argtypes = ci, [vp, ci, ctypes.c_char_p, ci, ctypes.POINTER(c64)]
+    L.dt_engine_set_original_size.restype, L.dt_engine_set_original_size.argtypes = ci, [vp, cf, cf]
+    L.dt_engine_run.restype, L.dt_engine_run.argtypes = ci, [vp, vp, cf, ci, ci, vp]
+    L.dt_engine_count_launches.restype, L.dt_engine_count_launches.argtypes = ci, [vp, ci, ci]
+    L._engine_bound = True
+
+
+class Engine:
+    def __init__(self, arch="resnet50", batch=1, height=800, width=1216, pre_nms_top_n=1000, post_nms_top_n=1000,
+                 rpn_nms_thresh=0.7, rpn_min_size=0.0, num_classes=81, score_thresh=0.05, det_nms_thresh=0.5, max_dets=100,
+                 det_cap=100, use_mask=True, output_prob=True, emit_full_masks=False, passes=3, device="cuda:0"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("detectorch_b200.Engine needs a CUDA device (no CPU fallback)")
+        self.L = _lib.lib()
+        _bind_engine_api(self.L)
+        self.device = torch.device(device)
+        cfg = EngineConfig()
+        cfg.arch_blocks = (ctypes.c_int * 4)(*ARCH_BLOCKS[arch])
+        cfg.batch, cfg.height, cfg.width = batch, height, width
+        cfg.pre_nms_top_n, cfg.post_nms_top_n = pre_nms_top_n, post_nms_top_n
+        cfg.rpn_nms_thresh, cfg.rpn_min_size = rpn_nms_thresh, rpn_min_size
+        cfg.num_classes, cfg.score_thresh, cfg.det_nms_thresh = num_classes, score_thresh, det_nms_thresh
+        cfg.max_dets, cfg.det_cap = max_dets, det_cap
+        cfg.use_mask, cfg.output_prob, cfg.emit_full_masks, cfg.passes = int(use_mask), int(output_prob), int(emit_full_masks), passes
+        self.cfg = cfg
+        self.h = self.L.dt_engine_create(ctypes.byref(cfg))
+        if not self.h:
+            raise RuntimeError("dt_engine_create failed (see stderr)")
+        with torch.cuda.device(self.device):
+            self.weights = torch.empty((self.L.dt_engine_weight_bytes(self.h),), dtype=torch.uint8, device=self.device)
+            self.workspace = torch.zeros((self.L.dt_engine_workspace_bytes(self.h),), dtype=torch.uint8, device=self.device)
+            _lib.check(self.L.dt_engine_bind(self.h, self.weights.data_ptr(), self.workspace.data_ptr(), self._stream()), "dt_engine_bind")
+        self._views = {}
+        self.weights_loaded = False
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.dt_engine_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def load_state_dict(self, sd):
+        """sd: {reference state_dict name: tensor}.  Names that are not hot-path parameters are ignored."""
+        n = 0
+        for name, t in sd.items():
+            if not torch.is_tensor(t) or not t.dtype.is_floating_point:
+                continue
+            t = t.detach().to(self.device, torch.float32).contiguous()
+            r = self.L.dt_engine_load_param(self.h, name.encode(), t.data_ptr(), t.numel(), self._stream())
+            if r == 0:
+                raise RuntimeError("dt_engine_load_param(%s) failed" % name)
+            n += (r == 1)
+            torch.cuda.current_stream(self.device).synchronize()   # keep `t` alive until the pack kernel ran
+        _lib.check(self.L.dt_engine_finalize_weights(self.h, self._stream()), "dt_engine_finalize_weights")
+        self.weights_loaded = True
+        return n
+
+    def buffer(self, name):
+        """Zero-copy torch view of a named engine tensor."""
+        if name in self._views:
+            return self._views[name]
+        off, nd, dims, dt = ctypes.c_int64(), ctypes.c_int(), (ctypes.c_int * 5)(), ctypes.c_int()
+        if self.L.dt_engine_buffer(self.h, name.encode(), ctypes.byref(off), ctypes.byref(nd), ctypes.byref(dims), ctypes.byref(dt)) != 1:
+            raise KeyError(name)
+        shape = [dims[i] for i in range(nd.value)]
+        dtype = _DTYPES[dt.value]
+        n = 1
+        for s in shape:
+            n *= s
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        v = self.workspace[off.value:off.value + nbytes].view(dtype).view(shape)
+        self._views[name] = v
+        return v
+
+    def run(self, image=None, scaling_factor=1.0, first=0, last=None):
+        if not self.weights_loaded:
+            raise RuntimeError("Engine.run before load_state_dict")
+        if last is None:
+            last = ST_MASK_OUT if self.cfg.use_mask else ST_DETECT
+        ptr = 0
+        if image is not None:
+            if not image.is_cuda or image.dtype != torch.float32 or not image.is_contiguous():
+                raise RuntimeError("image must be a contiguous fp32 CUDA tensor [B,3,H,W]")
+            if tuple(image.shape) != (self.cfg.batch, 3, self.cfg.height, self.cfg.width):
+                raise RuntimeError("image shape %s does not match the engine (%d,3,%d,%d)" % (tuple(image.shape), self.cfg.batch, self.cfg.height, self.cfg.width))
+            ptr = image.data_ptr()
+        _lib.check(self.L.dt_engine_run(self.h, ptr, float(scaling_factor), int(first), int(last), self._stream()), "dt_engine_run")
+
+    def set_original_size(self, h, w):
+        self.L.dt_engine_set_original_size(self.h, float(h), float(w))
+
+    def count_launches(self, first=0, last=11):
+        return self.L.dt_engine_count_launches(self.h, first, last)

@@ -1,0 +1,254 @@
+"""Drop-in mirror of the reference model API (lib/model/detector.py:130-286): same constructor
+kwargs, same forward signature / return tuple, same attribute names (`model`, `conv_body`,
+`conv_head`, `rpn`, `bbox_head`, `classif_head`, `mask_head`), same state_dict names and the same
+Detectron-pkl loader entry point -- but forward() runs the fused sm_100a engine
+(detectorch_b200/csrc/capi_engine.cu) instead of torch.nn ops + host numpy.
+
+The torch modules below are PARAMETER CONTAINERS ONLY (so state_dict()/load_state_dict()/the pkl
+loader keep working); none of their forward() methods is ever called.
+
+Supported configuration this round: the FPN + RPN (+ '1up4convs' mask head) family
+(eval_faster_FPN.ipynb / eval_mask_FPN.ipynb constructor kwargs), ResNet-50/101.
+"""
+import numpy as np
+import torch
+import torchvision.models as models
+
+from ..engine import Engine, ST_TRUNK, ST_BOX_HEAD, ST_DETECT, ST_MASK_ROI_FEAT, ST_MASK_OUT
+from ..utils import result_utils as _result_utils
+
+
+class _FpnBody(torch.nn.Module):           # parameter container: detector.py:12-33
+    def __init__(self, conv_body, in_channels, fpn_layers):
+        super().__init__()
+        self.conv_body = conv_body
+        self.fpn_lateral = torch.nn.ModuleList([torch.nn.Conv2d(c, 256, 1) for c in in_channels])
+        self.fpn_output = torch.nn.ModuleList([torch.nn.Conv2d(256, 256, 3, padding=1) for _ in in_channels])
+        self.fpn_layers = fpn_layers
+
+
+class _TwoLayerMlp(torch.nn.Module):       # detector.py:54-59
+    def __init__(self):
+        super().__init__()
+        self.fc6 = torch.nn.Linear(256 * 7 * 7, 1024)
+        self.fc7 = torch.nn.Linear(1024, 1024)
+
+
+class _FourConv(torch.nn.Module):          # detector.py:67-74
+    def __init__(self):
+        super().__init__()
+        for i in range(1, 5):
+            setattr(self, "fcn%d" % i, torch.nn.Conv2d(256, 256, 3, padding=1))
+
+
+class _RpnHead(torch.nn.Module):           # detector.py:114-121
+    def __init__(self, in_channels, out_channels, n_anchors):
+        super().__init__()
+        self.conv_rpn = torch.nn.Conv2d(in_channels, out_channels, 3, padding=1)
+        self.rpn_cls_prob = torch.nn.Conv2d(out_channels, n_anchors, 1)
+        self.rpn_bbox_pred = torch.nn.Conv2d(out_channels, 4 * n_anchors, 1)
+
+
+class _MaskHead(torch.nn.Module):
+    """mask_head of the reference (detector.py:84-112); forward(x, rois, roi_original_idx) keeps its signature."""
+
+    def __init__(self, owner, output_prob):
+        super().__init__()
+        self.conv_head = _FourConv()
+        self.transposed_conv = torch.nn.ConvTranspose2d(256, 256, 2, stride=2)
+        self.classif_logits = torch.nn.Conv2d(256, 81, 1)
+        self.output_prob = output_prob
+        self.roi_height = self.roi_width = 14
+        object.__setattr__(self, "_owner", owner)
+
+    def forward(self, x, rois, roi_original_idx=None):
+        return self._owner._run_mask_head(x, rois, roi_original_idx)
+
+
+class detector(torch.nn.Module):
+    def __init__(self,
+                 train=False,
+                 arch='resnet50',
+                 conv_body_layers=['conv1', 'bn1', 'relu', 'maxpool', 'layer1', 'layer2', 'layer3'],
+                 conv_head_layers=['layer4', 'avgpool'],
+                 fpn_layers=[],
+                 fpn_extra_lvl=True,
+                 use_rpn_head=False,
+                 use_mask_head=False,
+                 mask_head_type='upshare',
+                 roi_feature_channels=2048,
+                 N_classes=81,
+                 detector_pkl_file=None,
+                 base_cnn_pkl_file=None,
+                 output_prob=True,
+                 roi_height=14,
+                 roi_width=14,
+                 roi_spatial_scale=0.0625,
+                 roi_sampling_ratio=0):
+        super(detector, self).__init__()
+        self.roi_height, self.roi_width = int(roi_height), int(roi_width)
+        self.roi_spatial_scale = [float(i) for i in roi_spatial_scale] if isinstance(roi_spatial_scale, list) else float(roi_spatial_scale)
+        self.roi_sampling_ratio = int(roi_sampling_ratio)
+        self.train = train           # shadows nn.Module.train exactly like the reference (detector.py:159)
+        self.arch = arch
+        self.mask_head_type = mask_head_type
+        self.use_fpn_body = len(fpn_layers) > 0
+        self.fpn_extra_lvl = fpn_extra_lvl
+        self.use_rpn_head = use_rpn_head
+        self.use_mask_head = use_mask_head
+        self.use_two_layer_mlp_head = conv_head_layers == 'two_layer_mlp'
+        self.output_prob = output_prob
+        self.N_classes = N_classes
+        supported = (self.use_fpn_body and self.use_rpn_head and self.use_two_layer_mlp_head and fpn_extra_lvl and
+                     list(fpn_layers) == ['layer1', 'layer2', 'layer3', 'layer4'] and self.roi_height == 7 and self.roi_width == 7 and
+                     self.roi_sampling_ratio == 2 and self.roi_spatial_scale == [0.25, 0.125, 0.0625, 0.03125] and
+                     (not use_mask_head or mask_head_type == '1up4convs') and arch in ('resnet50', 'resnet101') and not train)
+        if not supported:
+            raise NotImplementedError("detectorch_b200 (round 1) implements the FPN+RPN(+1up4convs mask) inference family "
+                                      "(eval_faster_FPN / eval_mask_FPN kwargs); C4 configurations are not built yet")
+        if arch.startswith('resnet'):
+            self.model = getattr(models, arch)()
+        else:
+            raise NotImplementedError('Only resnet implemented so far!')
+        self.conv_body = _FpnBody(torch.nn.Sequential(*[getattr(self.model, l) for l in conv_body_layers]), (256, 512, 1024, 2048), fpn_layers)
+        self.conv_head = _TwoLayerMlp()
+        self.rpn = _RpnHead(256, 256, 3)
+        # with the two-layer MLP head the RoI feature is 1024-d (detector.py:143,212 default of 2048 only fits the C4 head)
+        feat = 1024 if self.use_two_layer_mlp_head else roi_feature_channels
+        self.bbox_head = torch.nn.Linear(feat, 4 * N_classes)
+        self.classif_head = torch.nn.Linear(feat, N_classes)
+        if self.use_mask_head:
+            self.mask_head = _MaskHead(self, output_prob)
+        self._engines = {}
+        self._engine = None
+        self._weights_version = 0
+        if detector_pkl_file is not None:
+            self.load_pretrained_weights(detector_pkl_file, model='detector')
+        elif base_cnn_pkl_file is not None:
+            self.load_pretrained_weights(base_cnn_pkl_file, model='base_cnn')
+        self.model.eval()
+
+    # ------------------------------------------------------------------ weights
+    def load_pretrained_weights(self, caffe_pkl_file, model='detector'):
+        """Detectron caffe2-pickle import (detector.py:289-374).  'Next' row of SURVEY.md 8f; needs
+        utils.utils.parse_th_to_caffe2 from the reference tree on sys.path."""
+        import pickle
+        from utils.utils import parse_th_to_caffe2   # reference helper (utils/utils.py:44-71)
+        with open(caffe_pkl_file, 'rb') as f:
+            blobs = pickle.load(f, encoding='latin1')
+        if model == 'detector':
+            blobs = blobs['blobs']
+        sd = self.model.state_dict()
+        for k in sd.keys():
+            if 'running' in k or 'fc' in k or 'num_batches' in k:
+                continue
+            kc = parse_th_to_caffe2(k.split('.'))
+            w = torch.FloatTensor(blobs[kc])
+            sd[k] = w[:, (2, 1, 0), :, :] if k == 'conv1.weight' else w     # BGR -> RGB
+        self.model.load_state_dict(sd)
+        if model == 'detector':
+            def put(mod, wn, bn):
+                mod.weight.data = torch.FloatTensor(blobs[wn]); mod.bias.data = torch.FloatTensor(blobs[bn])
+            put(self.bbox_head, 'bbox_pred_w', 'bbox_pred_b'); put(self.classif_head, 'cls_score_w', 'cls_score_b')
+            put(self.rpn.conv_rpn, 'conv_rpn_fpn2_w', 'conv_rpn_fpn2_b')
+            put(self.rpn.rpn_cls_prob, 'rpn_cls_logits_fpn2_w', 'rpn_cls_logits_fpn2_b')
+            put(self.rpn.rpn_bbox_pred, 'rpn_bbox_pred_fpn2_w', 'rpn_bbox_pred_fpn2_b')
+            if self.use_mask_head:
+                put(self.mask_head.transposed_conv, 'conv5_mask_w', 'conv5_mask_b')
+                put(self.mask_head.classif_logits, 'mask_fcn_logits_w', 'mask_fcn_logits_b')
+                for i in range(1, 5):
+                    put(getattr(self.mask_head.conv_head, 'fcn%d' % i), '_[mask]_fcn%d_w' % i, '_[mask]_fcn%d_b' % i)
+            for i, l in enumerate(self.conv_body.fpn_layers):
+                kc = parse_th_to_caffe2((l + '.' + list(getattr(self.model, l).state_dict().keys())[-1]).split('.'))
+                kc = kc[:kc.rfind("_")]
+                suffix = '_sum_lateral' if i < len(self.conv_body.fpn_layers) - 1 else '_sum'
+                put(self.conv_body.fpn_lateral[i], 'fpn_inner_' + kc + suffix + '_w', 'fpn_inner_' + kc + suffix + '_b')
+                put(self.conv_body.fpn_output[i], 'fpn_' + kc + '_sum_w', 'fpn_' + kc + '_sum_b')
+            put(self.conv_head.fc6, 'fc6_w', 'fc6_b'); put(self.conv_head.fc7, 'fc7_w', 'fc7_b')
+        self._weights_version += 1
+
+    def load_state_dict(self, state_dict, strict=True):
+        r = super().load_state_dict(state_dict, strict)
+        self._weights_version += 1
+        return r
+
+    # ------------------------------------------------------------------ engine plumbing
+    def engine_for(self, batch, h, w, **overrides):
+        key = (batch, h, w, tuple(sorted(overrides.items())))
+        ent = self._engines.get(key)
+        if ent is None or ent[1] != self._weights_version:
+            dev = next(self.parameters()).device
+            if dev.type != 'cuda':
+                raise RuntimeError("detectorch_b200.detector runs on CUDA only: call model.cuda() first (no CPU fallback)")
+            kw = dict(arch=self.arch, batch=batch, height=h, width=w, num_classes=self.N_classes, use_mask=self.use_mask_head,
+                      output_prob=self.output_prob, emit_full_masks=True, det_cap=128, device=dev)
+            kw.update(overrides)
+            eng = Engine(**kw)
+            eng.load_state_dict(self.state_dict())
+            ent = (eng, self._weights_version)
+            self._engines[key] = ent
+        return ent[0]
+
+    def forward(self, image, rois=None, scaling_factor=None, roi_original_idx=None):
+        """-> (cls_score [R,81], bbox_pred [R,324], rois [R,4], img_features [P2..P5])   detector.py:233-286.
+        Batch 1 like the reference; `detect()` below is the batched fused path."""
+        if rois is not None:
+            raise NotImplementedError("pre-computed proposals (Fast R-CNN) are not built yet")
+        if image.size(0) != 1:
+            raise RuntimeError("detector.forward keeps the reference's batch-1 contract; use detector.detect for batches")
+        sf = float(scaling_factor.reshape(-1)[0]) if torch.is_tensor(scaling_factor) else float(1.0 if scaling_factor is None else scaling_factor)
+        eng = self.engine_for(1, image.size(2), image.size(3))
+        self._engine = eng
+        self._last_sf = sf
+        _result_utils.set_active_engine(eng)
+        eng.run(image.contiguous().float(), sf, ST_TRUNK, ST_BOX_HEAD)
+        n = int(eng.buffer("roi_counts")[0].item())
+        cls_score = eng.buffer("cls_prob")[:n]
+        bbox_pred = eng.buffer("bbox_pred")[:n]
+        out_rois = eng.buffer("rois")[0, :n, 1:5]
+        feats = [eng.buffer("P%d" % l).permute(0, 3, 1, 2) for l in (2, 3, 4, 5)]     # NCHW-shaped views of the NHWC maps
+        return (cls_score, bbox_pred, out_rois, feats)
+
+    def _run_mask_head(self, img_features, rois, roi_original_idx):
+        eng = self._engine
+        if eng is None:
+            raise RuntimeError("mask_head called before forward")
+        # per-level lists -> original order (detector.py:103-106)
+        lv, parts = [], []
+        for i, r in enumerate(rois):
+            if r is None or len(r) == 0:
+                continue
+            r = r.to(eng.device).float()
+            if r.size(1) == 5:
+                r = r[:, 1:5]
+            parts.append(r)
+            lv.append(torch.full((r.size(0),), i, dtype=torch.int32, device=eng.device))
+        cat, lvl = torch.cat(parts, 0), torch.cat(lv, 0)
+        if roi_original_idx is not None:
+            idx = roi_original_idx.to(eng.device).long()
+            cat, lvl = cat[idx], lvl[idx]
+        n = cat.size(0)
+        mr, ml = eng.buffer("mask_rois"), eng.buffer("mask_levels")
+        if n > mr.size(0):
+            raise RuntimeError("mask_head: %d RoIs exceed the engine capacity %d" % (n, mr.size(0)))
+        mr.zero_(); ml.zero_()
+        mr[:n, 1:5] = cat
+        ml[:n] = lvl
+        eng.run(None, self._last_sf, ST_MASK_ROI_FEAT, ST_MASK_OUT)
+        return eng.buffer("masks_full")[:n]
+
+    # ------------------------------------------------------------------ fused batched path
+    def detect(self, images, scaling_factor=1.0, with_masks=None):
+        """Fused path: images [B,3,H,W] -> dict of padded per-image detections (boxes [B,cap,4], scores, classes, counts,
+        masks [B,cap,28,28] of the detected class).  No host synchronisation inside."""
+        eng = self.engine_for(images.size(0), images.size(2), images.size(3))
+        self._engine = eng
+        self._last_sf = float(scaling_factor)
+        with_masks = self.use_mask_head if with_masks is None else with_masks
+        eng.run(images.contiguous().float(), float(scaling_factor), ST_TRUNK, ST_MASK_OUT if with_masks else ST_DETECT)
+        B, cap = images.size(0), eng.cfg.det_cap
+        out = {"boxes": eng.buffer("det_boxes"), "scores": eng.buffer("det_scores"), "classes": eng.buffer("det_classes"),
+               "counts": eng.buffer("det_counts"), "roi_idx": eng.buffer("det_roi_idx")}
+        if with_masks:
+            out["masks"] = eng.buffer("masks").view(B, cap, 28, 28)
+        return out

@@ -1,0 +1,105 @@
+"""Torch-tensor front-ends of the C-ABI operators.  Torch is only plumbing here (device memory,
+current stream); all compute happens in detectorch_b200/csrc.  Every function requires CUDA
+tensors -- there is no CPU path."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise TypeError("detectorch_b200 operators run on CUDA tensors only (no CPU fallback)")
+
+
+def roi_align_forward_nchw(features, rois, pooled_height, pooled_width, spatial_scale, sampling_ratio, out=None):
+    """features [B,C,H,W] fp32 contiguous, rois [R,4|5] -> [R,C,ph,pw].  Mirrors
+    roialign.roi_align_forward_cuda of the reference (lib/model/roi_align.py:46-63)."""
+    _need_cuda(features, rois)
+    if features.dim() != 4 or rois.dim() != 2 or rois.size(1) not in (4, 5):
+        raise RuntimeError("roi_align: features must be [B,C,H,W] and rois [R,4|5]")
+    if not (features.is_contiguous() and rois.is_contiguous()):
+        raise RuntimeError("roi_align: features and rois must be contiguous")   # reference AT_CHECK, roi_align_forward_cuda.cu:189
+    if features.dtype != torch.float32 or rois.dtype != torch.float32:
+        raise RuntimeError("roi_align: fp32 only")
+    R, C = rois.size(0), features.size(1)
+    if out is None:
+        out = torch.empty((R, C, pooled_height, pooled_width), device=features.device, dtype=torch.float32)
+    ok = _lib.lib().dt_roi_align_forward_nchw(_p(features), _p(rois), R, rois.size(1), C, features.size(2), features.size(3),
+                                              int(pooled_height), int(pooled_width), float(spatial_scale), int(sampling_ratio),
+                                              _p(out), _stream())
+    _lib.check(ok, "dt_roi_align_forward_nchw")
+    return out
+
+
+def roi_align_forward_nhwc(feats, scales, rois, level, pooled_height, pooled_width, sampling_ratio, num_rois=None):
+    """feats: list of NHWC maps [B,H,W,C]; rois [R,5]; level int32 [R] or None -> out [R,ph,pw,C]."""
+    _need_cuda(rois, *feats)
+    n = len(feats)
+    ptrs = (ctypes.c_void_p * n)(*[f.data_ptr() for f in feats])
+    hs = (ctypes.c_int * n)(*[f.size(1) for f in feats])
+    ws = (ctypes.c_int * n)(*[f.size(2) for f in feats])
+    sc = (ctypes.c_float * n)(*[float(s) for s in scales])
+    C = feats[0].size(3)
+    R = rois.size(0)
+    out = torch.empty((R, pooled_height, pooled_width, C), device=rois.device, dtype=torch.float32)
+    ok = _lib.lib().dt_roi_align_forward_nhwc(ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(hs, ctypes.c_void_p),
+                                              ctypes.cast(ws, ctypes.c_void_p), ctypes.cast(sc, ctypes.c_void_p), n, _p(rois),
+                                              _p(level), _p(num_rois), R, C, pooled_height, pooled_width, sampling_ratio, _p(out),
+                                              _stream())
+    _lib.check(ok, "dt_roi_align_forward_nhwc")
+    return out
+
+
+def nms(dets, thresh):
+    """dets [N,5] fp32 CUDA (x1,y1,x2,y2,score) -> int64 CUDA tensor of ascending kept indices
+    (the contract of lib/utils/boxes.py:332-336)."""
+    _need_cuda(dets)
+    n = dets.size(0)
+    if n == 0:
+        return torch.zeros((0,), dtype=torch.int64, device=dets.device)
+    dets = dets.contiguous().float()
+    L = _lib.lib()
+    ws = torch.empty((L.dt_nms_workspace_bytes(n),), dtype=torch.uint8, device=dets.device)
+    keep = torch.empty((n,), dtype=torch.int64, device=dets.device)
+    cnt = torch.zeros((1,), dtype=torch.int32, device=dets.device)
+    _lib.check(L.dt_nms(_p(dets), n, float(thresh), _p(keep), _p(cnt), _p(ws), _stream()), "dt_nms")
+    return keep[:int(cnt.item())]
+
+
+def tf32_residual(w):
+    lo = torch.empty_like(w)
+    _lib.check(_lib.lib().dt_tf32_residual(_p(w), _p(lo), w.numel(), _stream()), "dt_tf32_residual")
+    return lo
+
+
+def conv2d_nhwc(x, w_kmajor, scale, shift, kh, kw, pad, stride, w_lo=None, residual=None, up_src=None, relu=False, sigmoid_ch=0,
+                passes=3, force_block_n=0, out=None):
+    """x [N,H,W,Cin] fp32 (channels-last memory), w_kmajor [Cout, kh*kw*Cin] -> y [N,Ho,Wo,Cout]."""
+    _need_cuda(x, w_kmajor)
+    N, H, W, Cin = x.shape
+    Cout = w_kmajor.size(0)
+    if w_lo is None:
+        w_lo = tf32_residual(w_kmajor)
+    Ho = (H + 2 * pad - kh) // stride + 1
+    Wo = (W + 2 * pad - kw) // stride + 1
+    if out is None:
+        out = torch.empty((N, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
+    res_mode = 1 if residual is not None else (2 if up_src is not None else 0)
+    up_h = up_src.size(1) if up_src is not None else 0
+    up_w = up_src.size(2) if up_src is not None else 0
+    ok = _lib.lib().dt_conv2d_nhwc(_p(x), N, H, W, Cin, Cin, _p(w_kmajor), _p(w_lo), Cout, kh, kw, pad, stride, _p(scale), _p(shift),
+                                   _p(residual), res_mode, _p(up_src), up_h, up_w, int(relu), int(sigmoid_ch), int(passes),
+                                   int(force_block_n), _p(out), Cout, _stream())
+    _lib.check(ok, "dt_conv2d_nhwc")
+    return out

@@ -1,0 +1,134 @@
+/*
+ * detectorch_b200 -- C ABI of the B200-native two-stage-detector inference hot path.
+ *
+ * Plain pointers and sizes only (no torch types).  Every pointer is a DEVICE pointer unless
+ * stated otherwise; every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ * never synchronises, and returns 1 on success / 0 on failure (the reference's launcher
+ * convention, lib/cppcuda_cffi/src/cuda/roi_align_forward_cuda_kernel.cu:161-199), printing the
+ * reason to stderr.  Layouts are fp32 throughout.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference
+ * repository root).  INTEGRATION.md shows the reference-side binding for each.
+ */
+#ifndef DETECTORCH_B200_H
+#define DETECTORCH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dt_stream_t; /* cudaStream_t */
+
+/* ---------------------------------------------------------------------------------------------
+ * RoIAlign forward.
+ * Replaces: lib/cppcuda_cffi/src/cuda/roi_align_forward_cuda_kernel.h:7-19 (exact signature kept:
+ * this symbol is what lib/cppcuda_cffi/src/roi_align_forward_cuda.c:35-47 calls), and through it
+ * lib/cppcuda/roi_align_cuda.h:4-11 / lib/model/roi_align.py:32-89.
+ * bottom_data NCHW [B,C,H,W]; bottom_rois [R,5] (batch,x1,y1,x2,y2); top_data [R,C,ph,pw];
+ * outputElements = R*C*ph*pw (int, as in the reference: < 2^31).
+ */
+int launch_roi_align_forward_cuda(const int outputElements, const float* bottom_data, const float* bottom_rois,
+                                  const float spatial_scale, const int channels, const int height, const int width,
+                                  const int pooled_height, const int pooled_width, const int sampling_ratio, float* top_data,
+                                  dt_stream_t stream);
+
+/* 64-bit-safe variant (R*C*ph*pw may exceed 2^31, e.g. 100k RoIs x 256 ch x 14 x 14); roi_cols is 4 or 5
+ * like the reference CPU loop (lib/cppcuda_cffi/src/cpp/roi_align_cpu_loop.h:5-17). */
+int dt_roi_align_forward_nchw(const float* features, const float* rois, int64_t num_rois, int roi_cols, int channels, int height,
+                              int width, int pooled_height, int pooled_width, float spatial_scale, int sampling_ratio, float* out,
+                              dt_stream_t stream);
+
+/* Multi-level NHWC variant used inside the fused detector (replaces the 4 per-level RoIAlign calls + cat +
+ * index-restore of lib/model/detector.py:259-270 and :100-106).  feats[l] is an NHWC map [B,H[l],W[l],C];
+ * rois [max_rois,5]; level[max_rois] (index into feats, NULL = all level 0); num_rois_dev: optional device int
+ * (rows >= *num_rois_dev are written as zeros); out [max_rois, ph, pw, C]. */
+int dt_roi_align_forward_nhwc(const float* const* feats_host_array, const int* heights, const int* widths, const float* scales,
+                              int num_levels, const float* rois, const int* level, const int* num_rois_dev, int max_rois,
+                              int channels, int pooled_height, int pooled_width, int sampling_ratio, float* out, dt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Greedy hard NMS with the reference's exact fp32 semantics ("+1" widths, ovr >= thresh).
+ * Replaces: lib/utils/boxes.py:332-336 -> lib/utils_cython/cython_nms.pyx:37-87.
+ * dets [n,5] (x1,y1,x2,y2,score).  keep_out [n] int64 receives the ASCENDING ORIGINAL indices of the
+ * survivors, *num_keep_out (device int) their count.  workspace: dt_nms_workspace_bytes(n) bytes.
+ */
+int64_t dt_nms_workspace_bytes(int64_t n);
+int dt_nms(const float* dets, int n, float thresh, int64_t* keep_out, int* num_keep_out, void* workspace, dt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Convolution / GEMM on tcgen05 tensor cores (3xTF32, fp32-accurate), NHWC activations.
+ * Replaces the torch.nn.Conv2d / Linear / ConvTranspose2d calls of lib/model/detector.py
+ * (:17-27 FPN, :58-59 FC6/FC7, :71-74 mask convs, :89-90 deconv + mask logits, :119-121 RPN, :170-183 trunk).
+ *   x        [N,H,W,Cin]   (Cin % 32 == 0), x_pix_stride floats between pixels
+ *   w        [Cout][kh][kw][Cin] fp32, w_lo = w - trunc_tf32(w) (dt_tf32_residual)
+ *   y        [N,Ho,Wo,Cout] (Cout % 4 == 0), y = act( conv(x,w)*scale[c] + shift[c] (+ residual) )
+ *   res_mode 0 none | 1 residual [N,Ho,Wo,Cout] | 2 nearest-2x-upsampled up_src [N,up_h,up_w,Cout]
+ *   relu     0/1 ; sigmoid_ch: channels [0,sigmoid_ch) get a sigmoid ; passes 3 (3xTF32) or 1 (TF32)
+ */
+int dt_tf32_residual(const float* w, float* w_lo, int64_t n, dt_stream_t stream);
+int dt_conv2d_nhwc(const float* x, int N, int H, int W, int Cin, int x_pix_stride, const float* w, const float* w_lo, int Cout,
+                   int kh, int kw, int pad, int stride, const float* scale, const float* shift, const float* residual,
+                   int res_mode, const float* up_src, int up_h, int up_w, int relu, int sigmoid_ch, int passes, int force_block_n,
+                   float* y, int y_pix_stride, dt_stream_t stream);
+
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused Mask R-CNN (ResNet-50/101 + FPN) inference engine: the whole of
+ *   lib/model/detector.py:233-286 (detector.forward), lib/utils/result_utils.py:76-168
+ *   (postprocess_output) and lib/model/detector.py:99-112 (mask_head.forward)
+ * as one static, sync-free program of sm_100a kernels.  The caller owns two flat device buffers
+ * (weights, workspace); named intermediate / output tensors are exposed as (offset, shape) into the
+ * workspace so the host language wraps them without copies.
+ */
+typedef struct dt_engine_config {
+    int arch_blocks[4];          /* bottlenecks per stage: {3,4,6,3} = ResNet-50, {3,4,23,3} = ResNet-101 */
+    int batch, height, width;    /* network input [batch,3,height,width], height/width multiples of 32 */
+    int pre_nms_top_n;           /* per-level RPN top-k before NMS (1000, detector.py:206)  */
+    int post_nms_top_n;          /* per-level and collected RoI count (1000, detector.py:207) */
+    float rpn_nms_thresh;        /* 0.7 (generate_proposals.py:28) */
+    float rpn_min_size;          /* 0   (generate_proposals.py:17) */
+    int num_classes;             /* 81 */
+    float score_thresh;          /* 0.05 (result_utils.py:98) */
+    float det_nms_thresh;        /* 0.5  (result_utils.py:99) */
+    int max_dets;                /* 100  (result_utils.py:106) */
+    int det_cap;                 /* padded detections per image in the fused outputs (>= max_dets) */
+    int use_mask;                /* build the '1up4convs' mask head */
+    int output_prob;             /* softmax / sigmoid on the outputs (detector.py:147) */
+    int emit_full_masks;         /* also materialise masks_full [D,num_classes,28,28] (the public layout) */
+    int passes;                  /* 3 = 3xTF32 (fp32-accurate, default), 1 = single-pass TF32 */
+} dt_engine_config;
+
+typedef void* dt_engine_t;
+
+dt_engine_t dt_engine_create(const dt_engine_config* cfg);
+void dt_engine_destroy(dt_engine_t e);
+int64_t dt_engine_weight_bytes(dt_engine_t e);
+int64_t dt_engine_workspace_bytes(dt_engine_t e);
+/* attach caller-owned device memory and build the launch program (TMA descriptors) */
+int dt_engine_bind(dt_engine_t e, void* weights, void* workspace, dt_stream_t stream);
+/* load one parameter by its reference state_dict name (torch layout, e.g. conv [Cout,Cin,kh,kw]); BN gains are
+ * folded as g/sqrt(1+1e-5) (detector.py:231,301).  returns 1 loaded, 2 ignored (not on the hot path), 0 error */
+int dt_engine_load_param(dt_engine_t e, const char* name, const float* src_dev, int64_t numel, dt_stream_t stream);
+int dt_engine_finalize_weights(dt_engine_t e, dt_stream_t stream);
+/* named buffer -> byte offset into the workspace, shape (<=5 dims), dtype (0 f32, 1 i32, 2 u8) */
+int dt_engine_buffer(dt_engine_t e, const char* name, int64_t* byte_offset, int* ndim, int* dims5, int* dtype);
+int dt_engine_num_stages(void);
+/* the hot-path parameter table: reference state_dict names and element counts */
+int dt_engine_param_count(dt_engine_t e);
+int dt_engine_param_info(dt_engine_t e, int i, char* name_out, int name_cap, int64_t* numel);
+/* original (un-scaled) image size used by the detection clip (result_utils.py:86); 0,0 = network size / scaling_factor */
+int dt_engine_set_original_size(dt_engine_t e, float orig_h, float orig_w);
+/* stages: 0 trunk, 1 FPN, 2 RPN convs, 3 proposals, 4 collect, 5 RoIAlign(box), 6 box head, 7 detect (decode+NMS+limit),
+ *         8 mask RoIs, 9 RoIAlign(mask), 10 mask convs, 11 mask output */
+int dt_engine_run(dt_engine_t e, const float* image_nchw, float scaling_factor, int first_stage, int last_stage, dt_stream_t stream);
+int dt_engine_count_launches(dt_engine_t e, int first_stage, int last_stage);
+
+/* library / build info */
+const char* dt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
