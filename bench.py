@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of Mask R-CNN R-50-FPN inference @ 3x800x1216, 1000 proposals, 100 detections
+(BASELINE.json `metric`, configs[2]: batch 8 per B200), one process per GPU.
+
+  python bench.py --gpus 1 --steps 20 --warmup 3            # our arm (sm_100a engine)
+  python bench.py --impl reference --steps 2 --warmup 1     # reference arm: the reference path on the host cores
+
+A "step" = one pass of the whole hot path (trunk, FPN, RPN, proposals, RoIAlign, box head, per-class NMS,
+mask head) over one batch of synthetic images.  `value` is timed with inputs resident in HBM; `e2e` is the
+same metric through the public call (detector.detect) with HOST pinned inputs: H2D copy of the images and
+D2H read of the detections + masks inside the timed region.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec Mask R-CNN R-50-FPN @800x1216, 1k proposals"
+WORKLOAD = "Mask R-CNN R-50-FPN inference, batch 8 per GPU, 3x800x1216 fp32, 1000 proposals/img, 100 dets/img (BASELINE.json configs[2])"
+GFLOP_PER_IMAGE = 490.5          # algorithmic 2*MAC per image for this config
+H, W, BATCH = 800, 1216, 8
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if r[1].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1400.0, "fallback"       # B200_PROFILING.md fallback figures
+
+
+# ----------------------------------------------------------------------------- reference arm / cpu baseline
+def cpu_reference_images_per_sec(steps, warmup, threads=None):
+    """The reference's CPU path for this workload: its detector graph under torch-CPU fp32 + its RoIAlign loop +
+    its greedy NMS + numpy post-processing, as restated in oracle/ (the reference tree does not exist on the GPU
+    box; oracle/_ref holds its compiled RoIAlign loop when it was built here).  One step = one image (bounded sample)."""
+    import torch
+    from oracle import network as net
+    n = threads or os.cpu_count() or 1
+    torch.set_num_threads(n)
+    P = net.synthetic_params("resnet50")
+    img = net.synthetic_image(1, H, W)
+    for _ in range(max(0, warmup)):
+        net.detect_and_mask_fpn(img, P)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        net.detect_and_mask_fpn(img, P)
+    dt = (time.perf_counter() - t0) / steps
+    return 1.0 / dt, dt, n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = min(args.steps, 3)
+    ips, dt, n = cpu_reference_images_per_sec(steps, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "note": "reference CPU path (torch-CPU fp32 graph + reference RoIAlign loop "
+                                                           "+ greedy NMS), 1 image per step (bounded sample of the batch-8 workload)"},
+            "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": n, "kind": "port", "sample": "%d x 1 image 3x800x1216" % steps},
+            "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from detectorch_b200.engine import Engine, ST_TRUNK, ST_MASK_OUT
+    from oracle import network as net      # synthetic weights / images only (shared seeded generator)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    eng = Engine(arch="resnet50", batch=BATCH, height=H, width=W, det_cap=100, use_mask=True, emit_full_masks=False, device=dev)
+    eng.load_state_dict(net.synthetic_params("resnet50"))
+    # distinct images per rank (weak scaling: 8 images per GPU); two host batches alternate so no step re-reads a hot input
+    host = [net.synthetic_image(BATCH, H, W, seed=10 * rank + i).pin_memory() for i in range(2)]
+    dimg = [h.to(dev, non_blocking=True) for h in host]
+    torch.cuda.synchronize()
+    launches_per_step = eng.count_launches(ST_TRUNK, ST_MASK_OUT)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- capture the step in a CUDA graph (one per resident input buffer)
+    graphs = []
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):
+        for i in range(2):
+            eng.run(dimg[i], 1.0)
+        side.synchronize()
+        for i in range(2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                eng.run(dimg[i], 1.0)
+            graphs.append(g)
+    torch.cuda.synchronize()
+
+    # ---- (A) device-resident throughput
+    for i in range(warmup):
+        graphs[i % 2].replay()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(steps):
+        graphs[i % 2].replay()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- (B) end to end through the device-facing call with HOST buffers: H2D of the images, D2H of the results
+    res_keys = ["det_boxes", "det_scores", "det_classes", "det_counts", "masks"]
+    res_dev = [eng.buffer(k) for k in res_keys]
+    res_host = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res_dev] for _ in range(2)]
+    h2d_bytes = host[0].numel() * 4
+    d2h_bytes = sum(t.numel() * t.element_size() for t in res_dev)
+    copy_s, comp_s = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    up_done = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_loop(n):
+        # two-deep pipeline: the H2D of step i+1 overlaps the compute of step i (separate copy stream);
+        # every step's inputs cross PCIe and every step's results are read back to pinned host memory.
+        for i in range(n):
+            b = i % 2
+            with torch.cuda.stream(copy_s):
+                copy_s.wait_event(free[b])
+                dimg[b].copy_(host[b], non_blocking=True)
+                up_done[b].record(copy_s)
+            with torch.cuda.stream(comp_s):
+                comp_s.wait_event(up_done[b])
+                graphs[b].replay()
+                free[b].record(comp_s)
+                for d, hbuf in zip(res_dev, res_host[b]):
+                    hbuf.copy_(d, non_blocking=True)
+        comp_s.synchronize()
+
+    for b in range(2):
+        free[b].record(comp_s)
+    e2e_loop(warmup)
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(comp_s)
+    e2e_loop(steps)
+    e1.record(comp_s)
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+
+    # ---- max over ranks
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms, e2e_wall_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms, e2e_wall_ms = t.tolist()
+    e2e_ms = max(e2e_ms, e2e_wall_ms)       # the copy stream's first upload precedes e0: take the wall clock bracket
+
+    # ---- roofline of the dominant kernel family (conv_tcgen05_kernel), measured live with CUDA events on the launch stream
+    roof, roi_roof, cpu_base = None, None, None
+    if rank == 0:
+        hbm_peak, bf16_peak, which = peaks()
+        prof = eng.profile(dimg[0], 1.0)
+        conv = [(m, f) for (m, f, st, bn) in prof if bn > 0]
+        conv_ms, conv_flops = sum(m for m, _ in conv), sum(f for _, f in conv)
+        all_ms = sum(m for (m, _, _, _) in prof)
+        tf32_peak = bf16_peak / 2.0          # kind::tf32 issues at half the kind::f16 rate (B200_PROFILING.md nominal 1.1 vs 2.25 PF)
+        ach = conv_flops / (conv_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "conv_tcgen05_kernel (85 launches/step)", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
+                "frac": ach / tf32_peak, "traffic": None,
+                "peak_source": "%s bf16_tflops_sustained/2 (tf32 MMA rate is half of bf16)" % which,
+                "executed_tflops": 3.0 * ach, "frac_executed": 3.0 * ach / tf32_peak,
+                "note": "achieved = algorithmic 2*MAC FLOPs of all conv/GEMM launches / their summed CUDA-event time; the kernel executes 3 TF32 MMAs "
+                        "per algorithmic product (3xTF32 fp32 emulation), frac_executed counts those",
+                "share_of_step": conv_ms / all_ms}
+        # RoIAlign (box head, 7x7): algorithmic bytes = output write + RoIs (maps are L2 resident)
+        roi = [m for (m, f, st, bn) in prof if st == 5]
+        roi_bytes = BATCH * 1000 * (49 * 256 * 4 + 20)
+        if roi:
+            gbs = roi_bytes / (roi[0] * 1e-3) / 1e9
+            roi_roof = {"bound": "hbm", "kernel": "roi_align_nhwc_kernel (box head)", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                        "traffic": None, "peak_source": which}
+        if not args.no_cpu_baseline:
+            ips, dt, n = cpu_reference_images_per_sec(1, 0)
+            cpu_base = {"value": ips, "unit": "images/sec", "cores": n, "kind": "port", "sample": "1 image 3x800x1216 (1/8 of one step), oracle/network.py"}
+
+    if rank == 0:
+        total_images = BATCH * world * steps
+        value = total_images / (ms * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": "dp%d (images sharded, no data-path collective)" % world,
+                           "l2": "inputs alternate between two 93 MB batches and every step streams ~11 GB of activations (>> 126 MB L2)",
+                           "cuda_graph": True, "tflops_algorithmic": value * GFLOP_PER_IMAGE / 1e3},
+                "clocks": clocks,
+                "e2e": {"value": total_images / (e2e_ms * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                        "ms_per_step": e2e_ms / steps, "note": "pinned host images -> H2D -> fused engine -> D2H boxes/scores/classes/counts/masks, 2-deep pipeline"},
+                "gpu_launches": launches_per_step * steps,
+                "roofline": roof, "roofline_roialign": roi_roof, "cpu_baseline": cpu_base}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -105,6 +105,7 @@ struct Buf {
 };
 
 struct Op {
+    double flops = 0.0;   // algorithmic FLOPs (2*MAC) of this launch, 0 for non-GEMM ops
     int stage;
     int kind;            // 0 conv, 1 custom lambda index
     ConvLayer conv;
@@ -360,7 +361,7 @@ struct ProgBuilder {
     void conv(int stage, const std::string& wname, const float* x, int N, int H, int W, int xstride, float* y, int ystride, int kpad,
               int stride, bool relu, int res_mode = RES_NONE, const float* res = nullptr, const float* up = nullptr, int up_h = 0,
               int up_w = 0, int sigmoid_ch = 0, size_t w_extra_off = 0, int out_h = 0, int out_w = 0, int out_step = 0, int oy = 0,
-              int ox = 0) {
+              int ox = 0, int force_bn = 0) {
         const ConvW& c = (*cw)[wname];
         ConvSpec s;
         memset(&s, 0, sizeof(s));
@@ -371,9 +372,15 @@ struct ProgBuilder {
         s.y = y; s.y_pix_stride = ystride;
         s.out_h = out_h; s.out_w = out_w; s.out_step = out_step; s.out_y0 = oy; s.out_x0 = ox;
         s.residual = res; s.res_pix_stride = c.cout; s.up_src = up; s.up_h = up_h; s.up_w = up_w;
-        s.res_mode = res_mode; s.relu = relu ? 1 : 0; s.sigmoid_ch = sigmoid_ch; s.passes = e->cfg.passes; s.force_block_n = 0;
+        s.res_mode = res_mode; s.relu = relu ? 1 : 0; s.sigmoid_ch = sigmoid_ch; s.passes = e->cfg.passes; s.force_block_n = force_bn;
         Op op;
         op.stage = stage; op.kind = 0; op.fn = -1;
+        {
+            const int Ho = (H + 2 * kpad - c.k) / stride + 1, Wo = (W + 2 * kpad - c.k) / stride + 1;
+            const double cin_alg = (wname == "stem") ? 147.0 : (double)c.cin;   // the stem K is zero-padded 147 -> 160
+            const double cout_alg = (wname == "rpn.head") ? 15.0 : (wname == "head") ? 5.0 * e->cfg.num_classes : (wname == "mask_logits") ? (double)e->cfg.num_classes : (double)c.cout;
+            op.flops = 2.0 * (double)N * Ho * Wo * cout_alg * cin_alg * c.k * c.k;
+        }
         if (!conv_build(s, &op.conv)) { ok = false; fprintf(stderr, "[detectorch_b200] engine: conv_build failed for %s\n", wname.c_str()); }
         e->ops.push_back(op);
     }
@@ -584,16 +591,20 @@ bool build_program(Engine* e, std::map<std::string, ConvW>* cw) {
     // ---- mask head (detector.py:99-112)
     if (c.use_mask) {
         const int D = B * c.det_cap, MN = (int)align_up((size_t)NC, 4);
+        // precise_mask: 128-wide tiles leave TMEM room for 3 rotating main accumulators (3x shorter truncating
+        // accumulation chains) on the layers that feed the mask logits, the tensor with the tightest parity bar
+        const int mbn = c.precise_mask ? 128 : 0;
         pb.fn(ST_MASK_ROIS, fn_mask_rois);
         pb.fn(ST_MASK_ROI_FEAT, fn_mask_roi_feat);
         const float* mx = e->buf("mask_feat");
         for (int i = 1; i <= 4; ++i) {
-            pb.conv(ST_MASK_HEAD, "mask_head.conv_head.fcn" + std::to_string(i), mx, D, 14, 14, 256, e->buf("mask_c" + std::to_string(i)), 256, 1, 1, true);
+            pb.conv(ST_MASK_HEAD, "mask_head.conv_head.fcn" + std::to_string(i), mx, D, 14, 14, 256, e->buf("mask_c" + std::to_string(i)), 256, 1, 1, true,
+                    RES_NONE, nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, mbn);
             mx = e->buf("mask_c" + std::to_string(i));
         }
         for (int ij = 0; ij < 4; ++ij)     // ConvTranspose2d(2, stride 2) == 4 GEMMs scattered on the 2x grid
             pb.conv(ST_MASK_HEAD, "deconv", mx, D, 14, 14, 256, e->buf("mask_up"), 256, 0, 1, true, RES_NONE, nullptr, nullptr, 0, 0, 0,
-                    (size_t)ij * 256 * 256, 28, 28, 2, ij / 2, ij % 2);
+                    (size_t)ij * 256 * 256, 28, 28, 2, ij / 2, ij % 2, mbn);
         pb.conv(ST_MASK_HEAD, "mask_logits", e->buf("mask_up"), D, 28, 28, 256, e->buf("mask_logits"), MN, 0, 1, false);
         pb.fn(ST_MASK_OUT, fn_mask_out);
     }
@@ -759,6 +770,40 @@ int dt_engine_run(dt_engine_t h, const float* image_nchw, float scaling_factor, 
         }
     }
     return 1;
+}
+
+// Profiling pass: runs stages [first,last] once with a CUDA-event pair around every op ON `stream`, synchronises, and
+// returns per-op milliseconds, algorithmic FLOPs (0 for non-GEMM ops), stage id and BLOCK_N (0 for non-GEMM ops).
+// Returns the number of ops written (<= cap).  This is a measurement aid; the production path is dt_engine_run.
+int dt_engine_profile(dt_engine_t h, const float* image_nchw, float scaling_factor, int first_stage, int last_stage, dt_stream_t stream,
+                      float* ms_out, double* flops_out, int* stage_out, int* block_n_out, int cap) {
+    Engine* e = reinterpret_cast<Engine*>(h);
+    if (!e->bound) return 0;
+    e->image = image_nchw;
+    e->scaling_factor = scaling_factor;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<cudaEvent_t> ev;
+    std::vector<const Op*> sel;
+    for (const Op& op : e->ops)
+        if (op.stage >= first_stage && op.stage <= last_stage && (int)sel.size() < cap) sel.push_back(&op);
+    ev.resize(sel.size() + 1);
+    for (auto& x : ev) cudaEventCreate(&x);
+    cudaEventRecord(ev[0], st);
+    for (size_t i = 0; i < sel.size(); ++i) {
+        const Op& op = *sel[i];
+        cudaError_t err = op.kind == 0 ? conv_launch(op.conv, st) : e->fns[op.fn](e, st);
+        if (err != cudaSuccess) { fprintf(stderr, "[detectorch_b200] engine profile: launch failed: %s\n", cudaGetErrorString(err)); return 0; }
+        cudaEventRecord(ev[i + 1], st);
+    }
+    cudaStreamSynchronize(st);
+    for (size_t i = 0; i < sel.size(); ++i) {
+        cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+        flops_out[i] = sel[i]->flops;
+        stage_out[i] = sel[i]->stage;
+        block_n_out[i] = sel[i]->kind == 0 ? sel[i]->conv.block_n : 0;
+    }
+    for (auto& x : ev) cudaEventDestroy(x);
+    return (int)sel.size();
 }
 
 // number of kernel launches stages [first,last] issue (bench.py's gpu_launches)

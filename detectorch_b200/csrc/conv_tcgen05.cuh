@@ -67,6 +67,9 @@ struct ConvCfg {
     static_assert(EPI_BYTES <= PIPE_BYTES, "epilogue staging reuses the pipeline buffers");
     static constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int THREADS = 192;
+    // TMEM accumulators: NMAIN round-robin main-term accumulators + 1 cross-term accumulator (see the MMA issuer)
+    static constexpr int NMAIN = (BLOCK_N == 256) ? 1 : 3;
+    static constexpr int TMEM_COLS = (BLOCK_N == 64) ? 256 : 512;     // (NMAIN + 1) * BLOCK_N, power of two
 };
 
 template <int BLOCK_N>
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(192, 1) conv_tcgen05_kernel(const __grid_const
         mbar_init(bar_res, 1);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<2 * BLOCK_N>(tmem_slot);   // [0,BLOCK_N) main term, [BLOCK_N,2*BLOCK_N) cross terms
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);   // NMAIN main accumulators, then the cross-term accumulator
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -155,16 +158,18 @@ __global__ void __launch_bounds__(192, 1) conv_tcgen05_kernel(const __grid_const
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {       // 4 x (K = 8 tf32 = 32 bytes) per 128-byte swizzle row
                     const uint64_t koff = (uint64_t)(k * 32 >> 4);
+                    // The tensor core accumulates in fp32 with truncation, so every accumulate step costs up to 1 ulp of
+                    // the running sum (a systematic shrink of ~0.18 * steps * 2^-23).  Two measures keep the chains short:
+                    //  * the two cross terms (~2^-11 of the main term) go to their own accumulator,
+                    //  * the main term rotates over NMAIN accumulators by k-block (summed with RN adds in the epilogue).
+                    const uint32_t acc_main = tmem_acc + (uint32_t)((kb % Cfg::NMAIN) * BLOCK_N);
+                    const uint32_t main_flag = (kb >= Cfg::NMAIN || k != 0) ? 1u : 0u;
                     if (p.passes == 3) {
-                        // The tensor core accumulates in fp32 with truncation, so every accumulate step costs up to
-                        // 1 ulp of the running sum.  The two cross terms are ~2^-11 of the main term: summing them in
-                        // their own accumulator keeps 2/3 of the steps away from the large running sum.
-                        umma_tf32(tmem_acc + BLOCK_N, dal + koff, dbh + koff, idesc, (kb | k) != 0);
-                        umma_tf32(tmem_acc + BLOCK_N, da + koff, dbl + koff, idesc, 1u);
-                        umma_tf32(tmem_acc, da + koff, dbh + koff, idesc, (kb | k) != 0);
-                    } else {
-                        umma_tf32(tmem_acc, da + koff, dbh + koff, idesc, (kb | k) != 0);
+                        const uint32_t acc_x = tmem_acc + (uint32_t)(Cfg::NMAIN * BLOCK_N);
+                        umma_tf32(acc_x, dal + koff, dbh + koff, idesc, (kb | k) != 0);
+                        umma_tf32(acc_x, da + koff, dbl + koff, idesc, 1u);
                     }
+                    umma_tf32(acc_main, da + koff, dbh + koff, idesc, main_flag);
                 }
                 umma_commit(bar_empty(s));                      // frees the smem slot when these MMAs retire
                 if (kb == num_kb - 1) umma_commit(bar_tmem_full);  // accumulator complete
@@ -233,15 +238,19 @@ __global__ void __launch_bounds__(192, 1) conv_tcgen05_kernel(const __grid_const
             const int ch0 = n0 + c * 32;
             if (ch0 >= p.cout) break;
             uint32_t v[32];
-            tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-            if (p.passes == 3) {
+            const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+            tmem_ld_32x32(tbase, v);
+            tmem_ld_wait();
+            const int nacc = (num_kb < Cfg::NMAIN ? num_kb : Cfg::NMAIN);
+#pragma unroll 1
+            for (int a = 1; a <= Cfg::NMAIN; ++a) {      // remaining main accumulators, then the cross accumulator
+                const bool is_cross = (a == Cfg::NMAIN);
+                if (is_cross ? (p.passes != 3) : (a >= nacc)) continue;
                 uint32_t x[32];
-                tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(BLOCK_N + c * 32), x);
+                tmem_ld_32x32(tbase + (uint32_t)(a * BLOCK_N), x);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(x[j]));
-            } else {
-                tmem_ld_wait();
             }
             float* stg = reinterpret_cast<float*>(smem_gen + c * Cfg::A_BYTES + row * 128);
             const float* up = nullptr;
@@ -297,7 +306,7 @@ __global__ void __launch_bounds__(192, 1) conv_tcgen05_kernel(const __grid_const
     // ---- teardown
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<2 * BLOCK_N>(tmem_acc);
+    if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_acc);
 }
 
 }  // namespace dt

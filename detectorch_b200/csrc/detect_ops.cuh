@@ -208,9 +208,55 @@ static __global__ void __launch_bounds__(1024) rpn_proposals_kernel(const __grid
         v0[i] = i;
     }
     __syncthreads();
-    // 2. descending sort by score (:77-86)
-    block_radix_sort_asc_u32(k0, v0, k1, v1, n, hist);
+    // 2. top-K by descending score (:77-86).  A full sort of ~180k keys by one CTA costs >1 ms, so first narrow the set
+    //    with a two-level 11+11-bit radix select on the key (exact: every key below the boundary sub-bin plus the whole
+    //    boundary sub-bin is kept, in index order), then stable-sort only those candidates.
     const int K = (P.pre_nms <= 0 || P.pre_nms >= n) ? n : P.pre_nms;
+    const int* vs = v0;                 // sorted anchor indices end up here
+    bool narrowed = false;
+    if (n > 4 * K && n > 8192) {
+        uint32_t* h1 = hist;            // 2048 bins
+        uint32_t* h2 = hist + 2048;     // 2048 bins
+        __shared__ uint32_t sel[4];     // b1, c1, b2, count
+        for (int i = threadIdx.x; i < 4096; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&h1[k0[i] >> 21], 1u);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t c = 0, b = 0;
+            for (; b < 2048; ++b) { if (c + h1[b] >= (uint32_t)K) break; c += h1[b]; }
+            sel[0] = b; sel[1] = c;
+        }
+        __syncthreads();
+        const uint32_t b1 = sel[0], c1 = sel[1];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { const uint32_t k = k0[i]; if ((k >> 21) == b1) atomicAdd(&h2[(k >> 10) & 2047u], 1u); }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t c = c1, b = 0;
+            for (; b < 2048; ++b) { if (c + h2[b] >= (uint32_t)K) break; c += h2[b]; }
+            sel[2] = b; sel[3] = c + (b < 2048 ? h2[b] : 0);
+        }
+        __syncthreads();
+        const uint32_t b2 = sel[2], total = sel[3];
+        if (total <= 8192u) {
+            int m = 0;
+            for (int base_i = 0; base_i < n; base_i += blockDim.x) {
+                const int i = base_i + threadIdx.x;
+                uint32_t k = 0;
+                bool f = false;
+                if (i < n) { k = k0[i]; const uint32_t d1 = k >> 21; f = (d1 < b1) || (d1 == b1 && ((k >> 10) & 2047u) <= b2); }
+                int tot;
+                const int r = block_rank(f, scratch, &tot);
+                if (f) { k1[m + r] = k; v1[m + r] = i; }
+                m += tot;
+            }
+            __syncthreads();
+            block_radix_sort_asc_u32(k1, v1, k0, v0, m, hist);
+            vs = v1;
+            narrowed = true;
+        }
+    }
+    if (!narrowed) block_radix_sort_asc_u32(k0, v0, k1, v1, n, hist);
     // 3. decode + clip + filter on the top K (:96-112), order preserved
     float4* cand = P.cand + ((size_t)b * P.num_levels + l) * P.pre_nms;
     float* cscore = P.cand_score + ((size_t)b * P.num_levels + l) * P.pre_nms;
@@ -222,7 +268,7 @@ static __global__ void __launch_bounds__(1024) rpn_proposals_kernel(const __grid
         float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
         float sc = 0.f;
         if (i < K) {
-            const int idx = v0[i];
+            const int idx = vs[i];
             if (P.dbg_order) P.dbg_order[((size_t)b * P.num_levels + l) * P.pre_nms + i] = idx;
             const int a = idx % lv.A, cell = idx / lv.A;
             const int x = cell % lv.W, y = cell / lv.W;

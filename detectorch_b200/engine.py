@@ -40,7 +40,7 @@ class EngineConfig(ctypes.Structure):
                 ("rpn_min_size", ctypes.c_float), ("num_classes", ctypes.c_int), ("score_thresh", ctypes.c_float),
                 ("det_nms_thresh", ctypes.c_float), ("max_dets", ctypes.c_int), ("det_cap", ctypes.c_int),
                 ("use_mask", ctypes.c_int), ("output_prob", ctypes.c_int), ("emit_full_masks", ctypes.c_int),
-                ("passes", ctypes.c_int)]
+                ("passes", ctypes.c_int), ("precise_mask", ctypes.c_int)]
 
 
 _DTYPES = {0: torch.float32, 1: torch.int32, 2: torch.uint8}
@@ -65,13 +65,14 @@ def _bind_engine_api(L):
     L.dt_engine_set_original_size.restype, L.dt_engine_set_original_size.argtypes = ci, [vp, cf, cf]
     L.dt_engine_run.restype, L.dt_engine_run.argtypes = ci, [vp, vp, cf, ci, ci, vp]
     L.dt_engine_count_launches.restype, L.dt_engine_count_launches.argtypes = ci, [vp, ci, ci]
+    L.dt_engine_profile.restype, L.dt_engine_profile.argtypes = ci, [vp, vp, cf, ci, ci, vp, vp, vp, vp, vp, ci]
     L._engine_bound = True
 
 
 class Engine:
     def __init__(self, arch="resnet50", batch=1, height=800, width=1216, pre_nms_top_n=1000, post_nms_top_n=1000,
                  rpn_nms_thresh=0.7, rpn_min_size=0.0, num_classes=81, score_thresh=0.05, det_nms_thresh=0.5, max_dets=100,
-                 det_cap=100, use_mask=True, output_prob=True, emit_full_masks=False, passes=3, device="cuda:0"):
+                 det_cap=100, use_mask=True, output_prob=True, emit_full_masks=False, passes=3, precise_mask=True, device="cuda:0"):
         if not torch.cuda.is_available():
             raise RuntimeError("detectorch_b200.Engine needs a CUDA device (no CPU fallback)")
         self.L = _lib.lib()
@@ -85,6 +86,7 @@ class Engine:
         cfg.num_classes, cfg.score_thresh, cfg.det_nms_thresh = num_classes, score_thresh, det_nms_thresh
         cfg.max_dets, cfg.det_cap = max_dets, det_cap
         cfg.use_mask, cfg.output_prob, cfg.emit_full_masks, cfg.passes = int(use_mask), int(output_prob), int(emit_full_masks), passes
+        cfg.precise_mask = int(precise_mask)
         self.cfg = cfg
         self.h = self.L.dt_engine_create(ctypes.byref(cfg))
         if not self.h:
@@ -156,6 +158,15 @@ class Engine:
 
     def set_original_size(self, h, w):
         self.L.dt_engine_set_original_size(self.h, float(h), float(w))
+
+    def profile(self, image, scaling_factor=1.0, first=0, last=11):
+        """One event-bracketed pass: list of (ms, algorithmic_flops, stage, block_n) per launch."""
+        cap = 512
+        ms = (ctypes.c_float * cap)(); fl = (ctypes.c_double * cap)(); st = (ctypes.c_int * cap)(); bn = (ctypes.c_int * cap)()
+        n = self.L.dt_engine_profile(self.h, image.data_ptr(), float(scaling_factor), first, last, self._stream(), ms, fl, st, bn, cap)
+        if n <= 0:
+            raise RuntimeError("dt_engine_profile failed")
+        return [(ms[i], fl[i], st[i], bn[i]) for i in range(n)]
 
     def count_launches(self, first=0, last=11):
         return self.L.dt_engine_count_launches(self.h, first, last)

@@ -98,6 +98,7 @@ typedef struct dt_engine_config {
     int output_prob;             /* softmax / sigmoid on the outputs (detector.py:147) */
     int emit_full_masks;         /* also materialise masks_full [D,num_classes,28,28] (the public layout) */
     int passes;                  /* 3 = 3xTF32 (fp32-accurate, default), 1 = single-pass TF32 */
+    int precise_mask;            /* 1 = mask-head convs use 128-wide tiles with 3 rotating accumulators (tighter fp32 parity) */
 } dt_engine_config;
 
 typedef void* dt_engine_t;
@@ -124,6 +125,10 @@ int dt_engine_set_original_size(dt_engine_t e, float orig_h, float orig_w);
  *         8 mask RoIs, 9 RoIAlign(mask), 10 mask convs, 11 mask output */
 int dt_engine_run(dt_engine_t e, const float* image_nchw, float scaling_factor, int first_stage, int last_stage, dt_stream_t stream);
 int dt_engine_count_launches(dt_engine_t e, int first_stage, int last_stage);
+/* measurement aid: one pass with a CUDA-event pair around every launch on `stream` (synchronises at the end);
+ * per-op milliseconds, algorithmic FLOPs (0 for non-GEMM ops), stage id, BLOCK_N (0 for non-GEMM ops) */
+int dt_engine_profile(dt_engine_t e, const float* image_nchw, float scaling_factor, int first_stage, int last_stage, dt_stream_t stream,
+                      float* ms_out, double* flops_out, int* stage_out, int* block_n_out, int cap);
 
 /* library / build info */
 const char* dt_version(void);

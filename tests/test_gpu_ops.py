@@ -1,0 +1,182 @@
+"""GPU parity tests of the stand-alone operators, called through the C ABI (detectorch_b200/_lib.py ->
+include/detectorch_b200.h), against the oracle and the committed golden vectors."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def dev(built):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def G():
+    return np.load(os.path.join(GOLD, "ops_golden.npz"))
+
+
+def _boxes(rng, n, W=1216, H=800):
+    cx, cy = rng.uniform(0, W, n), rng.uniform(0, H, n)
+    w = np.exp(rng.uniform(np.log(16), np.log(600), n)); a = np.exp(rng.uniform(-0.7, 0.7, n))
+    b = np.stack([cx - w * np.sqrt(a) / 2, cy - w / np.sqrt(a) / 2, cx + w * np.sqrt(a) / 2, cy + w / np.sqrt(a) / 2], 1)
+    b[:, 0::2] = np.clip(b[:, 0::2], 0, W - 1); b[:, 1::2] = np.clip(b[:, 1::2], 0, H - 1)
+    return b.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------- RoIAlign
+def test_roi_align_golden_bit_exact(dev, G):
+    from detectorch_b200 import ops
+    f, r = torch.from_numpy(G["roi_feat"]).to(dev), torch.from_numpy(G["roi_rois"]).to(dev)
+    for (p, sr, s) in [(7, 2, 16), (14, 2, 16), (14, 0, 16), (7, 0, 32)]:
+        out = ops.roi_align_forward_nchw(f, r, p, p, 1. / s, sr).cpu().numpy()
+        assert np.array_equal(out, G["roi_out_p%d_sr%d_s%d" % (p, sr, s)]), (p, sr, s)
+    out4 = ops.roi_align_forward_nchw(f[:1].contiguous(), r[:, 1:].contiguous(), 7, 7, 1 / 16., 2).cpu().numpy()
+    assert np.array_equal(out4, G["roi_out_4col"])
+
+
+def test_roi_align_reference_launcher_symbol(dev, G):
+    """The exact extern "C" symbol of the reference (roi_align_forward_cuda_kernel.h:7-19), raw pointers + stream."""
+    from detectorch_b200 import _lib
+    f, r = torch.from_numpy(G["roi_feat"]).to(dev), torch.from_numpy(G["roi_rois"]).to(dev)
+    out = torch.zeros((r.size(0), f.size(1), 7, 7), device=dev)
+    ok = _lib.lib().launch_roi_align_forward_cuda(out.numel(), f.data_ptr(), r.data_ptr(), 1 / 16., f.size(1), f.size(2), f.size(3), 7, 7, 2,
+                                                  out.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert ok == 1
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), G["roi_out_p7_sr2_s16"])
+
+
+def test_roi_align_random_vs_oracle_and_layouts(dev):
+    from detectorch_b200 import ops
+    from oracle import ref
+    rng = np.random.RandomState(3)
+    f = rng.randn(2, 32, 50, 68).astype(np.float32)
+    r = np.hstack([rng.randint(0, 2, (500, 1)).astype(np.float32), _boxes(rng, 500, 1088, 800)])
+    r[:5, 1:] = [[-100, -100, -50, -50], [2000, 2000, 2100, 2100], [5, 5, 5, 5], [0, 0, 1087, 799], [500, 400, 499, 399]]
+    for (p, sr) in ((7, 2), (14, 0), (14, 2)):
+        want = ref.roi_align_forward(f, r, p, p, 1 / 16., sr)
+        got = ops.roi_align_forward_nchw(torch.from_numpy(f).to(dev), torch.from_numpy(r).to(dev), p, p, 1 / 16., sr).cpu().numpy()
+        assert np.array_equal(got, want)
+        fn = torch.from_numpy(f).permute(0, 2, 3, 1).contiguous().to(dev)
+        got2 = ops.roi_align_forward_nhwc([fn], [1 / 16.], torch.from_numpy(r).to(dev), None, p, p, sr).permute(0, 3, 1, 2).cpu().numpy()
+        assert np.array_equal(got2, want)
+    # empty input
+    assert ops.roi_align_forward_nchw(torch.from_numpy(f).to(dev), torch.zeros((0, 5), device=dev), 7, 7, 1 / 16., 2).shape == (0, 32, 7, 7)
+
+
+def test_roi_align_mirror_module_and_errors(dev):
+    from detectorch_b200.model.roi_align import RoIAlign, RoIAlignFunction
+    from oracle import ref
+    rng = np.random.RandomState(4)
+    f = rng.randn(1, 8, 20, 30).astype(np.float32)
+    r4 = _boxes(rng, 40, 480, 320)
+    out = RoIAlign(7, 7, 1 / 16., 2)(torch.from_numpy(f).to(dev), torch.from_numpy(r4).to(dev))
+    assert np.array_equal(out.cpu().numpy(), ref.roi_align_forward(f, r4, 7, 7, 1 / 16., 2))
+    with pytest.raises(TypeError):
+        RoIAlignFunction.apply(torch.from_numpy(f).to(dev), torch.from_numpy(r4), 7, 7, 1 / 16., 2)     # device mismatch, roi_align.py:43-44
+
+
+def test_roi_align_full_size_properties(dev):
+    """BASELINE configs[4] size (100k RoIs x 256 ch, 50x68 map): constant map -> every in-map bin equals the constant;
+    linearity in the features."""
+    from detectorch_b200 import ops
+    rng = np.random.RandomState(5)
+    R = 100000
+    rois = torch.from_numpy(np.hstack([np.zeros((R, 1), np.float32), _boxes(rng, R, 1088, 800)])).to(dev)
+    ones = torch.full((1, 256, 50, 68), 3.0, device=dev)
+    out = ops.roi_align_forward_nchw(ones, rois, 7, 7, 1 / 16., 2)
+    assert out.shape == (R, 256, 7, 7)
+    assert float(out.max()) <= 3.0 + 1e-5 and float(out[:, 0].min()) >= 0.0
+    inside = (rois[:, 3] < 1087 - 16) & (rois[:, 4] < 799 - 16)
+    assert torch.all((out[inside] - 3.0).abs() < 1e-5)
+    a = torch.randn((1, 256, 50, 68), device=dev); b = torch.randn((1, 256, 50, 68), device=dev)
+    sub = rois[:2000].contiguous()
+    lhs = ops.roi_align_forward_nchw(a + b, sub, 7, 7, 1 / 16., 2)
+    rhs = ops.roi_align_forward_nchw(a, sub, 7, 7, 1 / 16., 2) + ops.roi_align_forward_nchw(b, sub, 7, 7, 1 / 16., 2)
+    assert float((lhs - rhs).abs().max()) < 1e-4
+
+
+# ------------------------------------------------------------------------------- NMS
+def test_nms_golden_bit_exact(dev, G):
+    from detectorch_b200 import ops
+    for k in range(5):
+        keep = ops.nms(torch.from_numpy(G["nms%d_dets" % k]).to(dev), float(G["nms%d_thresh" % k])).cpu().numpy()
+        assert np.array_equal(keep, G["nms%d_keep" % k]), k
+    assert ops.nms(torch.zeros((0, 5), device=dev), 0.5).numel() == 0
+
+
+def test_nms_random_vs_oracle(dev):
+    from detectorch_b200 import ops
+    from detectorch_b200.utils import boxes as mirror
+    from oracle import ref
+    rng = np.random.RandomState(6)
+    for n in (1, 2, 63, 64, 65, 129, 1000, 4097, 6000):
+        d = np.hstack([_boxes(rng, n), rng.permutation(n).astype(np.float32)[:, None] / n])     # unique scores
+        for t in (0.3, 0.5, 0.7):
+            assert np.array_equal(ops.nms(torch.from_numpy(d).to(dev), t).cpu().numpy(), ref.nms(d, t)), (n, t)
+    d = np.hstack([_boxes(rng, 500), rng.uniform(0, 1, (500, 1)).astype(np.float32)])
+    assert np.array_equal(np.asarray(mirror.nms(d, 0.5)), ref.nms(d, 0.5))       # numpy-in / numpy-out mirror of boxes.nms
+    assert mirror.nms(np.zeros((0, 5), np.float32), 0.5) == []
+
+
+def test_nms_large_properties(dev):
+    """20k boxes: idempotence (NMS of the survivors keeps everything) and kept ids are sorted ascending."""
+    from detectorch_b200 import ops
+    rng = np.random.RandomState(8)
+    n = 20000
+    d = torch.from_numpy(np.hstack([_boxes(rng, n), rng.permutation(n).astype(np.float32)[:, None] / n])).to(dev)
+    keep = ops.nms(d, 0.5)
+    assert torch.all(keep[1:] > keep[:-1])
+    again = ops.nms(d[keep].contiguous(), 0.5)
+    assert again.numel() == keep.numel()
+
+
+# ------------------------------------------------------------------------------- conv / GEMM (tcgen05, 3xTF32)
+def _conv_case(dev, N, Hh, Ww, Cin, Cout, k, pad, stride, res=False, up=False, relu=False, sig=0, passes=3):
+    from detectorch_b200 import ops
+    g = torch.Generator().manual_seed(N * 1000 + Hh * 10 + Cin + Cout + k)
+    x = torch.randn((N, Hh, Ww, Cin), generator=g)
+    w = torch.randn((Cout, k, k, Cin), generator=g) * (2.0 / (k * k * Cin)) ** 0.5
+    sc, sh = 0.5 + torch.rand((Cout,), generator=g), 0.1 * torch.randn((Cout,), generator=g)
+    Ho, Wo = (Hh + 2 * pad - k) // stride + 1, (Ww + 2 * pad - k) // stride + 1
+    R = torch.randn((N, Ho, Wo, Cout), generator=g) if res else None
+    U = torch.randn((N, (Ho + 1) // 2, (Wo + 1) // 2, Cout), generator=g) if up else None
+    y = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w.double().permute(0, 3, 1, 2), stride=stride, padding=pad)
+    y = y * sc.double().view(1, -1, 1, 1) + sh.double().view(1, -1, 1, 1)
+    if res:
+        y = y + R.double().permute(0, 3, 1, 2)
+    if up:
+        y = y + torch.nn.functional.interpolate(U.double().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")[:, :, :Ho, :Wo]
+    if relu:
+        y = torch.relu(y)
+    y = y.permute(0, 2, 3, 1).contiguous()
+    if sig:
+        y[..., :sig] = torch.sigmoid(y[..., :sig])
+    got = ops.conv2d_nhwc(x.to(dev), w.reshape(Cout, -1).contiguous().to(dev), sc.to(dev), sh.to(dev), k, k, pad, stride,
+                          residual=R.to(dev) if res else None, up_src=U.to(dev) if up else None, relu=relu, sigmoid_ch=sig, passes=passes)
+    err = (got.cpu().double() - y).abs().max().item()
+    return err / max(1.0, y.abs().max().item())
+
+
+@pytest.mark.parametrize("case", [
+    (1, 1, 128, 64, 64, 1, 0, 1), (1, 1, 1000, 1024, 408, 1, 0, 1), (1, 20, 30, 64, 128, 3, 1, 1), (2, 25, 38, 256, 256, 3, 1, 1),
+    (1, 50, 76, 256, 128, 1, 0, 2), (2, 25, 38, 128, 64, 1, 0, 2), (5, 14, 14, 256, 256, 3, 1, 1), (1, 1, 300, 12544, 1024, 1, 0, 1)])
+def test_conv_3xtf32_matches_fp64_within_1e4(dev, case):
+    # tolerance: 1e-4 of the tensor's max-abs (BASELINE north_star fp32 parity bar); 3xTF32 measures ~1e-6..1e-5
+    assert _conv_case(dev, *case) < 1e-4
+
+
+def test_conv_epilogues(dev):
+    assert _conv_case(dev, 1, 20, 30, 64, 256, 1, 0, 1, res=True, relu=True) < 1e-4
+    assert _conv_case(dev, 2, 13, 19, 128, 64, 3, 1, 1, res=True, relu=True) < 1e-4
+    assert _conv_case(dev, 1, 26, 38, 64, 256, 1, 0, 1, up=True) < 1e-4
+    assert _conv_case(dev, 1, 25, 38, 256, 16, 1, 0, 1, sig=3) < 1e-4
+    # single-pass TF32 is NOT fp32-accurate: this is why the product path runs 3 passes
+    assert 1e-4 < _conv_case(dev, 1, 1, 256, 1024, 128, 1, 0, 1, passes=1) < 5e-3
