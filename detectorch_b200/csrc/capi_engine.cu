@@ -5,6 +5,7 @@
 // a static program of kernel launches over pre-built TMA descriptors, with zero host synchronisation
 // (the reference syncs >= 17 times per image).  Memory is supplied by the caller as two
 // flat device buffers (weights, workspace) so that the host language (PyTorch here) stays pure plumbing.
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -42,6 +43,14 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, int rows, int Ki
         const int r = (int)(i / Kout);
         dst[i] = k < Kin ? src[(size_t)r * Kin + k] : 0.f;
     }
+}
+// stem [64][3][7][7] -> [64][7 (ky)][32 (kx*4 + c; kx < 7, c < 3; rest 0)]  (fused-window stem, conv_build_stem)
+__global__ void pack_stem_window_kernel(const float* __restrict__ src, float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 64 * 224) return;
+    const int j = i % 32, ky = (i / 32) % 7, o = i / 224;
+    const int kx = j >> 2, c = j & 3;
+    dst[i] = (kx < 7 && c < 3) ? src[((o * 3 + c) * 7 + ky) * 7 + kx] : 0.f;
 }
 // fc6 [O][C*P] (k = c*P + p) -> [O][P*C] (k = p*C + c)
 __global__ void pack_fc6_kernel(const float* __restrict__ src, int O, int C, int P, float* __restrict__ dst) {
@@ -135,6 +144,8 @@ struct Engine {
     float orig_h = 0.f, orig_w = 0.f;   // original image size for the final clip (0 = network size / scaling_factor)
     // static geometry
     int H1, W1, H2, W2;                 // stem out, pool out
+    int Hp, Wp;                         // padded NHWC4 stem input
+    bool stem_fused = true;
     int LH[5], LW[5];                   // P2..P6
     RpnParams rpn;
     CollectParams col;
@@ -184,7 +195,7 @@ void build_param_table(Engine* e, std::map<std::string, ConvW>* cw) {
     // stem
     {
         ConvW c; c.cout = 64; c.cin = 160; c.k = 1;
-        c.w = add_mat(e, "model.conv1.weight", PK_STEM_W, 64, 160, 64, 147, 160, 0);
+        c.w = add_mat(e, "model.conv1.weight", PK_STEM_W, 64, 160 + 224, 64, 147, 160, 0);   // im2col layout [64][160], then window layout [64][224]
         c.scale = add_vec(e, "model.bn1.weight", PK_BN_SCALE, 64, 64);
         c.shift = add_vec(e, "model.bn1.bias", PK_VEC, 64, 64);
         (*cw)["stem"] = c;
@@ -287,7 +298,9 @@ void plan_buffers(Engine* e) {
     const int B = c.batch;
     e->H1 = conv_out(c.height, 7, 2, 3); e->W1 = conv_out(c.width, 7, 2, 3);
     e->H2 = conv_out(e->H1, 3, 2, 1); e->W2 = conv_out(e->W1, 3, 2, 1);
-    add_buf(e, "stem_col", {(long long)B * e->H1 * e->W1, 160});
+    e->Hp = std::max(c.height + 6, 2 * e->H1 + 5); e->Wp = std::max(c.width + 6, 2 * e->W1 + 6);
+    add_buf(e, "stem_x4", {B, e->Hp, e->Wp, 4});
+    add_buf(e, "stem_col", {(long long)B * e->H1 * e->W1, 160});     // fallback path only (see build_program)
     add_buf(e, "c1", {B, e->H1, e->W1, 64});
     add_buf(e, "pool", {B, e->H2, e->W2, 64});
     int h = e->H2, w = e->W2;
@@ -372,7 +385,7 @@ struct ProgBuilder {
         s.y = y; s.y_pix_stride = ystride;
         s.out_h = out_h; s.out_w = out_w; s.out_step = out_step; s.out_y0 = oy; s.out_x0 = ox;
         s.residual = res; s.res_pix_stride = c.cout; s.up_src = up; s.up_h = up_h; s.up_w = up_w;
-        s.res_mode = res_mode; s.relu = relu ? 1 : 0; s.sigmoid_ch = sigmoid_ch; s.passes = e->cfg.passes; s.force_block_n = force_bn;
+        s.res_mode = res_mode; s.relu = relu ? 1 : 0; s.sigmoid_ch = sigmoid_ch; s.passes = e->cfg.passes; s.force_block_n = force_bn; s.precise = (force_bn == 128) ? 1 : 0;
         Op op;
         op.stage = stage; op.kind = 0; op.fn = -1;
         {
@@ -396,6 +409,11 @@ struct ProgBuilder {
 cudaError_t fn_stem_im2col(Engine* e, cudaStream_t s) {
     const long long n = (long long)e->cfg.batch * e->H1 * e->W1 * 40;
     stem_im2col_kernel<<<grid_for(n), 256, 0, s>>>(e->image, e->cfg.batch, e->cfg.height, e->cfg.width, e->H1, e->W1, e->buf("stem_col"));
+    return cudaGetLastError();
+}
+cudaError_t fn_stem_pack(Engine* e, cudaStream_t s) {
+    const long long n = (long long)e->cfg.batch * e->Hp * e->Wp;
+    stem_pack_nhwc4_kernel<<<grid_for(n), 256, 0, s>>>(e->image, e->cfg.batch, e->cfg.height, e->cfg.width, e->Hp, e->Wp, e->buf("stem_x4"));
     return cudaGetLastError();
 }
 cudaError_t fn_maxpool(Engine* e, cudaStream_t s) {
@@ -479,8 +497,24 @@ bool build_program(Engine* e, std::map<std::string, ConvW>* cw) {
     const int B = c.batch;
     ProgBuilder pb{e, cw};
     // ---- trunk (detector.py:170-183)
-    pb.fn(ST_TRUNK, fn_stem_im2col);
-    pb.conv(ST_TRUNK, "stem", e->buf("stem_col"), 1, 1, B * e->H1 * e->W1, 160, e->buf("c1"), 64, 0, 1, true);
+    {
+        // fused-window stem (no im2col buffer); falls back to im2col + GEMM if the driver rejects the overlapping-stride map
+        const ConvW& sw = (*cw)["stem"];
+        Op op;
+        op.stage = ST_TRUNK; op.kind = 0; op.fn = -1;
+        op.flops = 2.0 * (double)B * e->H1 * e->W1 * 64.0 * 147.0;
+        e->stem_fused = c.stem_im2col ? false
+                                      : conv_build_stem(e->buf("stem_x4"), B, e->Hp, e->Wp, e->H1, e->W1, e->wmat(sw.w + 64 * 160), e->wlo(sw.w + 64 * 160),
+                                                        e->wvec(sw.scale), e->wvec(sw.shift), e->buf("c1"), c.passes, &op.conv);
+        if (e->stem_fused) {
+            pb.fn(ST_TRUNK, fn_stem_pack);
+            e->ops.push_back(op);
+        } else {
+            if (!c.stem_im2col) fprintf(stderr, "[detectorch_b200] engine: fused stem descriptor rejected, using the im2col stem\n");
+            pb.fn(ST_TRUNK, fn_stem_im2col);
+            pb.conv(ST_TRUNK, "stem", e->buf("stem_col"), 1, 1, B * e->H1 * e->W1, 160, e->buf("c1"), 64, 0, 1, true);
+        }
+    }
     pb.fn(ST_TRUNK, fn_maxpool);
     const float* x = e->buf("pool");
     int h = e->H2, w = e->W2, cin = 64;
@@ -631,7 +665,10 @@ int load_param(Engine* e, const std::string& name, const float* src, long long n
     }
     switch (s.kind) {
         case PK_CONV_W: pack_conv_w_kernel<<<grid_for(numel), 256, 0, st>>>(src, s.d0, s.d1, s.d2, s.d3, e->wmat(s.off)); break;
-        case PK_STEM_W: pack_rows_kernel<<<grid_for((long long)s.d0 * s.d2), 256, 0, st>>>(src, s.d0, s.d1, s.d2, e->wmat(s.off)); break;
+        case PK_STEM_W:
+            pack_rows_kernel<<<grid_for((long long)s.d0 * s.d2), 256, 0, st>>>(src, s.d0, s.d1, s.d2, e->wmat(s.off));
+            pack_stem_window_kernel<<<(64 * 224 + 255) / 256, 256, 0, st>>>(src, e->wmat(s.off) + 64 * 160);
+            break;
         case PK_FC6_W: pack_fc6_kernel<<<grid_for(numel), 256, 0, st>>>(src, s.d0, s.d1, s.d2, e->wmat(s.off)); break;
         case PK_ROWS_W: pack_rows_kernel<<<grid_for(numel), 256, 0, st>>>(src, s.d0, s.d1, s.d1, e->wmat(s.off) + (size_t)s.row_off * s.Kout); break;
         case PK_DECONV_W: pack_deconv_kernel<<<grid_for(numel), 256, 0, st>>>(src, s.d0, s.d1, e->wmat(s.off)); break;

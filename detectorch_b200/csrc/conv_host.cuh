@@ -71,6 +71,7 @@ inline bool make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_
 struct ConvLayer {
     ConvParams p;
     int block_n;
+    int nmain = 1;      // rotating main-term accumulators (3 = precise: shorter truncating accumulation chains)
     dim3 grid;
     bool valid = false;
 };
@@ -90,6 +91,7 @@ struct ConvSpec {
     const float* up_src; int up_h, up_w;          // RES_UPSAMPLE2X
     int res_mode, relu, sigmoid_ch, passes;
     int force_block_n;                            // 0 = auto
+    int precise;                                  // BLOCK_N == 128 only: 3 rotating accumulators instead of TMEM double-buffering
 };
 
 inline void choose_box(int Wo, int Ho, int N, int max_w, int* wbox, int* hbox, int* nbox) {
@@ -107,6 +109,20 @@ inline void choose_box(int Wo, int Ho, int N, int max_w, int* wbox, int* hbox, i
         }
     }
     *wbox = bw; *hbox = bh; *nbox = bn;
+}
+
+// Persistent launch geometry: work items = (pairs of M-tiles) x (N-tiles); one 2-CTA cluster per SM pair (74 on B200),
+// each looping over items pair, pair + num_pairs, ...  An odd M-tile count gets one all-out-of-range surplus tile (TMA
+// zero-fills its loads and clips its stores) so that both CTAs of a pair always run the same multicast protocol.
+inline void finish_grid(ConvLayer* L, int n_tiles) {
+    ConvParams& p = L->p;
+    const int mtiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    p.m_pairs = (mtiles + 1) / 2;
+    p.n_tiles = n_tiles;
+    const int items = p.m_pairs * p.n_tiles;
+    const int pairs = items < kNumSMs / 2 ? items : kNumSMs / 2;
+    L->grid = dim3((unsigned)(2 * pairs), 1, 1);
+    L->valid = true;
 }
 
 inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
@@ -128,8 +144,9 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
     if (!make_tmap_4d(&p.tm_a, s.x, s.Cin, s.W, s.H, s.N, xs, xs * s.W, xs * s.W * s.H, 32, wbox * s.stride, hbox * s.stride, nbox,
                       s.stride, s.stride))
         return false;
-    if (!make_tmap_2d(&p.tm_bhi, s.w_hi, K, s.Cout, (uint64_t)K * 4, 32, bn)) return false;
-    if (!make_tmap_2d(&p.tm_blo, s.w_lo ? s.w_lo : s.w_hi, K, s.Cout, (uint64_t)K * 4, 32, bn)) return false;
+    // each CTA of a pair fetches half of the BLOCK_N weight rows and multicasts them
+    if (!make_tmap_2d(&p.tm_bhi, s.w_hi, K, s.Cout, (uint64_t)K * 4, 32, bn / 2)) return false;
+    if (!make_tmap_2d(&p.tm_blo, s.w_lo ? s.w_lo : s.w_hi, K, s.Cout, (uint64_t)K * 4, 32, bn / 2)) return false;
     const uint64_t ys = (uint64_t)s.y_pix_stride * 4;
     if (s.out_step == 0) {
         if (!make_tmap_4d(&p.tm_d, s.y, s.Cout, Wo, Ho, s.N, ys, ys * Wo, ys * Wo * Ho, 32, wbox, hbox, nbox)) return false;
@@ -147,7 +164,7 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
     p.scale = s.scale; p.shift = s.shift;
     p.up_src = s.up_src; p.up_h = s.up_h; p.up_w = s.up_w;
     p.cin_blocks = s.Cin / 32;
-    p.kh = s.kh; p.kw = s.kw; p.pad = s.pad; p.stride = s.stride;
+    p.kh = s.kh; p.kw = s.kw; p.pad_w = p.pad_h = s.pad; p.stride_w = p.stride_h = s.stride;
     p.tiles_w = ceil_div(Wo, wbox); p.tiles_h = ceil_div(Ho, hbox); p.tiles_n = ceil_div(s.N, nbox);
     p.wbox = wbox; p.hbox = hbox; p.nbox = nbox;
     p.wo = Wo; p.ho = Ho; p.nimg = s.N;
@@ -155,29 +172,61 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
     p.a_tile_bytes = wbox * hbox * nbox * 128;
     p.relu = s.relu; p.sigmoid_ch = s.sigmoid_ch; p.res_mode = s.res_mode;
     p.passes = s.passes == 1 ? 1 : 3;
-    L->grid = dim3((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n), (unsigned)ceil_div(s.Cout, bn), 1);
-    L->valid = true;
+    L->nmain = (bn == 64) ? 3 : ((bn == 128 && s.precise) ? 3 : 1);
+    finish_grid(L, ceil_div(s.Cout, bn));
     return true;
 }
 
-template <int BN>
-inline cudaError_t conv_launch_bn(const ConvLayer& L, cudaStream_t stream) {
+// The 7x7 stride-2 stem (3 input channels) as an implicit GEMM without an im2col buffer: the image is repacked once as
+// zero-bordered NHWC4 [B, Hp, Wp, 4]; for filter row ky the 7 taps x 4 channels of an output pixel are 28 CONTIGUOUS floats
+// starting at padded pixel 2*ow, so a TMA descriptor whose "pixel" dimension has an OVERLAPPING stride of 8 floats
+// (2 pixels) delivers, per ky, one 32-float K-block per output pixel straight into the swizzled A tile (last 4 floats
+// hit zero weights).  K = 7 x 32.  H uses elementStride 2.
+inline bool conv_build_stem(const float* x4, int B, int Hp, int Wp, int H1, int W1, const float* w_hi, const float* w_lo, const float* scale,
+                            const float* shift, float* y, int passes, ConvLayer* L) {
+    memset(&L->p, 0, sizeof(ConvParams));
+    ConvParams& p = L->p;
+    int wbox, hbox, nbox;
+    choose_box(W1, H1, B, 256, &wbox, &hbox, &nbox);
+    const int bn = 64;
+    L->block_n = bn;
+    const uint64_t row = (uint64_t)Wp * 16;
+    if (!make_tmap_4d(&p.tm_a, x4, 32, W1, Hp, B, 32, row, row * Hp, 32, wbox, hbox * 2, nbox, 1, 2)) return false;
+    if (!make_tmap_2d(&p.tm_bhi, w_hi, 224, 64, 224 * 4, 32, bn / 2)) return false;
+    if (!make_tmap_2d(&p.tm_blo, w_lo, 224, 64, 224 * 4, 32, bn / 2)) return false;
+    const uint64_t ys = 64 * 4;
+    if (!make_tmap_4d(&p.tm_d, y, 64, W1, H1, B, ys, ys * W1, ys * W1 * H1, 32, wbox, hbox, nbox)) return false;
+    p.scale = scale; p.shift = shift;
+    p.cin_blocks = 1; p.kh = 7; p.kw = 1;
+    p.pad_w = 0; p.pad_h = 0; p.stride_w = 1; p.stride_h = 2;
+    p.tiles_w = ceil_div(W1, wbox); p.tiles_h = ceil_div(H1, hbox); p.tiles_n = ceil_div(B, nbox);
+    p.wbox = wbox; p.hbox = hbox; p.nbox = nbox;
+    p.wo = W1; p.ho = H1; p.nimg = B; p.cout = 64;
+    p.a_tile_bytes = wbox * hbox * nbox * 128;
+    p.relu = 1; p.sigmoid_ch = 0; p.res_mode = RES_NONE; p.passes = passes == 1 ? 1 : 3;
+    L->nmain = 3;
+    finish_grid(L, 1);
+    return true;
+}
+
+template <int BN, int NM>
+inline cudaError_t conv_launch_cfg(const ConvLayer& L, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN>::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel<BN, NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN, NM>::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    conv_tcgen05_kernel<BN><<<L.grid, ConvCfg<BN>::THREADS, ConvCfg<BN>::SMEM_BYTES, stream>>>(L.p);
+    conv_tcgen05_kernel<BN, NM><<<L.grid, ConvCfg<BN, NM>::THREADS, ConvCfg<BN, NM>::SMEM_BYTES, stream>>>(L.p);
     return cudaGetLastError();
 }
 
 inline cudaError_t conv_launch(const ConvLayer& L, cudaStream_t stream) {
     if (!L.valid) return cudaErrorInvalidValue;
     switch (L.block_n) {
-        case 64: return conv_launch_bn<64>(L, stream);
-        case 128: return conv_launch_bn<128>(L, stream);
-        case 256: return conv_launch_bn<256>(L, stream);
+        case 64: return conv_launch_cfg<64, 3>(L, stream);
+        case 128: return L.nmain == 3 ? conv_launch_cfg<128, 3>(L, stream) : conv_launch_cfg<128, 1>(L, stream);
+        case 256: return conv_launch_cfg<256, 1>(L, stream);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -43,6 +43,23 @@ static __global__ void stem_im2col_kernel(const float* __restrict__ img, int B, 
     }
 }
 
+// image NCHW [B,3,H,W] -> zero-bordered NHWC4 [B,Hp,Wp,4] (3-pixel border = the conv1 padding; channel 3 = 0)
+static __global__ void stem_pack_nhwc4_kernel(const float* __restrict__ img, int B, int H, int W, int Hp, int Wp, float* __restrict__ x4) {
+    const long long total = (long long)B * Hp * Wp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int xp = (int)(i % Wp);
+        const int yp = (int)((i / Wp) % Hp);
+        const int b = (int)(i / ((long long)Wp * Hp));
+        const int x = xp - 3, y = yp - 3;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x >= 0 && x < W && y >= 0 && y < H) {
+            const size_t o = ((size_t)b * 3 * H + y) * W + x;
+            v.x = __ldg(img + o); v.y = __ldg(img + o + (size_t)H * W); v.z = __ldg(img + o + 2 * (size_t)H * W);
+        }
+        reinterpret_cast<float4*>(x4)[i] = v;
+    }
+}
+
 // NHWC 3x3 stride-2 pad-1 max pool (torchvision maxpool)
 static __global__ void maxpool3x3s2_nhwc_kernel(const float* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo, float* __restrict__ y) {
     const int C4 = C >> 2;

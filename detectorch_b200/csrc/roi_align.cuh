@@ -150,6 +150,45 @@ static __global__ void __launch_bounds__(256) roi_align_nhwc_kernel(RoiLevels lv
         __syncthreads();
         const float count = (float)(g.grid_h * g.grid_w);
         const float4* fb = reinterpret_cast<const float4*>(lv.feat[l] + (size_t)g.batch * H * W * C);
+        if (tabled && g.grid_h == 2 && g.grid_w == 2) {
+            // sampling_ratio == 2 (every FPN RoIAlign): all 16 tap loads of a bin are issued before any arithmetic
+            // (memory-level parallelism), then combined in exactly the reference order.
+            for (int o = threadIdx.x; o < per_roi; o += blockDim.x) {
+                const int c4 = o % C4;
+                const int bin = o / C4;
+                const int pw = bin % PW, ph = bin / PW;
+                AxisTap ty[2], tx[2];
+                ty[0] = ytab[ph * 2]; ty[1] = ytab[ph * 2 + 1];
+                tx[0] = xtab[pw * 2]; tx[1] = xtab[pw * 2 + 1];
+                float4 v[2][2][4];
+#pragma unroll
+                for (int iy = 0; iy < 2; ++iy)
+#pragma unroll
+                    for (int ix = 0; ix < 2; ++ix) {
+                        v[iy][ix][0] = __ldg(fb + ((size_t)ty[iy].lo * W + tx[ix].lo) * C4 + c4);
+                        v[iy][ix][1] = __ldg(fb + ((size_t)ty[iy].lo * W + tx[ix].hi) * C4 + c4);
+                        v[iy][ix][2] = __ldg(fb + ((size_t)ty[iy].hi * W + tx[ix].lo) * C4 + c4);
+                        v[iy][ix][3] = __ldg(fb + ((size_t)ty[iy].hi * W + tx[ix].hi) * C4 + c4);
+                    }
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int iy = 0; iy < 2; ++iy)
+#pragma unroll
+                    for (int ix = 0; ix < 2; ++ix) {
+                        if (ty[iy].valid && tx[ix].valid) {
+                            const float w1 = __fmul_rn(ty[iy].wl, tx[ix].wl), w2 = __fmul_rn(ty[iy].wl, tx[ix].wh);
+                            const float w3 = __fmul_rn(ty[iy].wh, tx[ix].wl), w4 = __fmul_rn(ty[iy].wh, tx[ix].wh);
+#define DT_TAP(f)                                                                                                     \
+    acc.f = __fadd_rn(acc.f, __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v[iy][ix][0].f), __fmul_rn(w2, v[iy][ix][1].f)), \
+                                                   __fmul_rn(w3, v[iy][ix][2].f)), __fmul_rn(w4, v[iy][ix][3].f)));
+                            DT_TAP(x) DT_TAP(y) DT_TAP(z) DT_TAP(w)
+#undef DT_TAP
+                        }
+                    }
+                ob[o] = make_float4(__fdiv_rn(acc.x, count), __fdiv_rn(acc.y, count), __fdiv_rn(acc.z, count), __fdiv_rn(acc.w, count));
+            }
+            continue;
+        }
         for (int o = threadIdx.x; o < per_roi; o += blockDim.x) {
             const int c4 = o % C4;
             const int bin = o / C4;

@@ -99,6 +99,7 @@ typedef struct dt_engine_config {
     int emit_full_masks;         /* also materialise masks_full [D,num_classes,28,28] (the public layout) */
     int passes;                  /* 3 = 3xTF32 (fp32-accurate, default), 1 = single-pass TF32 */
     int precise_mask;            /* 1 = mask-head convs use 128-wide tiles with 3 rotating accumulators (tighter fp32 parity) */
+    int stem_im2col;             /* 1 = force the im2col + GEMM stem instead of the fused TMA-window stem (debug) */
 } dt_engine_config;
 
 typedef void* dt_engine_t;

@@ -168,11 +168,35 @@ def timing(batch=8, h=800, w=1216, arch="resnet50", passes=3):
         batch, ms, batch * 1000.0 / ms, tot, passes, eng.buffer("roi_counts").cpu().tolist(), eng.buffer("det_counts").cpu().tolist()), flush=True)
 
 
+def ops(batch=8, h=800, w=1216, arch="resnet50", **kw):
+    P = net.synthetic_params(arch)
+    eng = E.Engine(arch=arch, batch=batch, height=h, width=w, **kw)
+    eng.load_state_dict(P)
+    img = net.synthetic_image(batch, h, w).to(dev)
+    for _ in range(3):
+        eng.run(img, 1.0)
+    torch.cuda.synchronize()
+    acc = None
+    reps = 5
+    for _ in range(reps):
+        pr = eng.profile(img, 1.0)
+        acc = [list(x) for x in pr] if acc is None else [[a[0] + b[0]] + a[1:] for a, b in zip(acc, pr)]
+    tot = sum(a[0] for a in acc) / reps
+    for i, (ms, fl, st, bn) in enumerate(acc):
+        ms /= reps
+        print("OP %3d stage %2d bn %3d  %9.1f us  %8.2f GFLOP  %7.1f TFLOP/s alg" % (i, st, bn, ms * 1e3, fl / 1e9, fl / (ms * 1e-3) / 1e12 if ms > 0 else 0), flush=True)
+    print("OPS total %.3f ms  %s" % (tot, kw), flush=True)
+
+
 if __name__ == "__main__":
     print("device:", torch.cuda.get_device_name(0), flush=True)
     mode = sys.argv[1]
     if mode == "parity":
         parity()
+    elif mode == "ops":
+        ops()
+    elif mode == "ops_im2col":
+        ops(stem_im2col=True)
     elif mode == "timing":
         timing(int(sys.argv[2]) if len(sys.argv) > 2 else 8, passes=int(sys.argv[3]) if len(sys.argv) > 3 else 3)
     print("==== done", flush=True)
