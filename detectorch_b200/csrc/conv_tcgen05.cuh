@@ -22,13 +22,14 @@
 // BLOCK_K = 32 fp32 = one 128-byte swizzle row.
 //
 // Execution model (round-1 profile: the one-tile-per-CTA version lost ~20k cycles per tile to prologue +
-// un-overlapped epilogue): PERSISTENT CTAs in 2-CTA clusters, 320 threads =
+// un-overlapped epilogue): PERSISTENT CTAs in 2-CTA clusters, 448 threads =
 //   warp 0      TMA producer (A tile; its half of the weight k-block, multicast to both CTAs of the pair)
 //   warp 1      TMEM owner + MMA issuer (one elected lane)
 //   warps 2-5   A_lo converters
-//   warps 6-9   epilogue: TMEM -> regs -> scale/shift [+residual] [ReLU|sigmoid] -> swizzled smem -> TMA store,
-//               32-channel chunks through a 2 x 16 KB staging ring that is NOT aliased with the pipeline,
-//               so the producer / converter / MMA warps run ahead into the next tile while a tile drains.
+//   warps 6-13  epilogue, two independent groups of 4 warps: TMEM -> regs -> scale/shift [+residual] [ReLU|sigmoid] ->
+//               swizzled smem -> TMA store, 32-channel chunks (even chunks group 0, odd chunks group 1), each group with
+//               its own 16 KB staging slot that is NOT aliased with the pipeline, so the producer / converter / MMA warps
+//               run ahead into the next tile while a tile drains.
 // TMEM holds NMAIN rotating main-term accumulators + 1 cross-term accumulator per tile, double-buffered
 // when two tiles fit in the 512 columns.
 #pragma once
@@ -78,14 +79,14 @@ struct ConvCfg {
     static constexpr int TMEM_COLS = (NBUF * TILE_COLS > 256) ? 512 : (NBUF * TILE_COLS > 128 ? 256 : 128);
     static constexpr int NUM_BARS = 3 * STAGES + 2 * NBUF + 2;
     static constexpr int SMEM_BYTES = PIPE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int THREADS = 320;
+    static constexpr int THREADS = 448;
     static_assert(TILE_COLS <= 512, "accumulators of one tile must fit TMEM");
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory limit");
     static_assert(8 * (NUM_BARS + 1) <= 256, "barrier area");
 };
 
 template <int BLOCK_N, int NMAIN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
     using Cfg = ConvCfg<BLOCK_N, NMAIN>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int NBUF = Cfg::NBUF;
@@ -102,7 +103,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) conv_tcgen05
     auto bar_empty = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };            // both CTAs' MMAs retired
     auto bar_tfull = [&](int b) { return bar_base + 8u * (3 * STAGES + b); };            // a tile's accumulators complete
     auto bar_tempty = [&](int b) { return bar_base + 8u * (3 * STAGES + NBUF + b); };    // ... drained by the epilogue
-    auto bar_res = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 * NBUF + b); };   // residual chunk landed in staging slot b
+    auto bar_res = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 * NBUF + b); };   // residual chunk landed in epilogue group b's slot
     const uint32_t tmem_slot = bar_base + 8u * Cfg::NUM_BARS;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(epi_gen + Cfg::EPI_BYTES + 8 * Cfg::NUM_BARS);
 
@@ -126,7 +127,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) conv_tcgen05
         }
         for (int b = 0; b < NBUF; ++b) {
             mbar_init(bar_tfull(b), 1);
-            mbar_init(bar_tempty(b), 128);
+            mbar_init(bar_tempty(b), 256);
         }
         mbar_init(bar_res(0), 1);
         mbar_init(bar_res(1), 1);
@@ -248,12 +249,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) conv_tcgen05
             }
         }
     } else {
-        // ================================================================ epilogue (128 threads, warps 6..9)
-        const int et = threadIdx.x - 192;       // 0..127
-        const int q = warp & 3;                 // TMEM lane quarter this warp may access (warps 6,7,8,9 -> 2,3,0,1)
-        const int row = q * 32 + lane;          // accumulator row == pixel slot in the box
+        // ================================================================ epilogue: two independent groups of 4 warps (warps 6-9, 10-13)
+        // Group g drains the live 32-channel chunks c with c % 2 == g through its own 16 KB staging slot, so two chunks are in
+        // flight per tile and every SM sub-partition has two epilogue warps to hide TMEM / shared / global latencies.
         constexpr int NCHUNK = BLOCK_N / 32;
-        uint32_t cc = 0;                        // live-chunk counter -> staging slot / residual-barrier phase
+        const int g = (warp - 6) >> 2;
+        const int et = threadIdx.x - 192 - 128 * g;   // 0..127 within the group
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;          // accumulator row == pixel slot in the box
+        const uint32_t slot = epi_base + g * Cfg::A_BYTES;
+        uint8_t* slot_gen = epi_gen + g * Cfg::A_BYTES;
+        uint32_t gc = 0;                        // chunks this group has processed -> residual-barrier phase
         int t = 0;
         for (int item = pair; item < num_items; item += num_pairs, ++t) {
             int w0, h0, n0img, n0;
@@ -262,7 +268,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) conv_tcgen05
             const int nacc = (num_kb < NMAIN ? num_kb : NMAIN);
             int nlive = (p.cout - n0 + 31) / 32;       // chunks past the true Cout are neither computed nor stored
             nlive = nlive < 0 ? 0 : (nlive > NCHUNK ? NCHUNK : nlive);
-            // pixel coordinates of this row (only needed for the upsample residual)
+            // pixel coordinates of this row (needed for the upsample operand)
             int pw_ = 0, ph_ = 0, pn_ = 0;
             bool row_valid = false;
             if (p.res_mode == RES_UPSAMPLE2X) {
@@ -275,20 +281,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) conv_tcgen05
             mbar_wait(bar_tfull(buf), ((uint32_t)(t / NBUF)) & 1u);
             tc_fence_after();
             const uint32_t tbase0 = tmem_acc + (uint32_t)(buf * Cfg::TILE_COLS) + ((uint32_t)(q * 32) << 16);
-            if (nlive == 0) { tc_fence_before(); mbar_arrive(bar_tempty(buf)); }
+            int last_c = -1;                             // this group's last live chunk of the tile
+            for (int c = g; c < nlive; c += 2) last_c = c;
+            if (last_c < 0) { tc_fence_before(); mbar_arrive(bar_tempty(buf)); }
 #pragma unroll 1
-            for (int c = 0; c < nlive; ++c, ++cc) {
+            for (int c = g; c < nlive; c += 2, ++gc) {
                 const int ch0 = n0 + c * 32;
-                const uint32_t sb = cc & 1u;
-                // staging slot sb was last used two chunks ago: its TMA store must have finished READING it
+                // upsample operand of this chunk: requested from global BEFORE the TMEM reads (latency overlap)
+                float4 rr[8];
+                {
+                    const float* rp = nullptr;
+                    if (p.res_mode == RES_UPSAMPLE2X && row_valid) {
+                        const int uy = min((h0 + ph_) >> 1, p.up_h - 1), ux = min((w0 + pw_) >> 1, p.up_w - 1);
+                        rp = p.up_src + (((size_t)(n0img + pn_) * p.up_h + uy) * p.up_w + ux) * (size_t)p.cout + ch0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        rr[j] = (rp != nullptr && ch0 + j * 4 < p.cout) ? __ldg(reinterpret_cast<const float4*>(rp) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                // the group's previous TMA store must have finished READING the slot; then the residual tile chunk (RES_TILE)
+                // is landed in the slot by TMA (hardware clipping / zero fill handles the tile edges)
                 if (et == 0) {
-                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    tma_store_wait_read0();
                     if (p.res_mode == RES_TILE) {
-                        mbar_arrive_expect_tx(bar_res(sb), (uint32_t)p.a_tile_bytes);
-                        tma_load_4d(epi_base + sb * Cfg::A_BYTES, &p.tm_r, bar_res(sb), ch0, w0, h0, n0img);
+                        mbar_arrive_expect_tx(bar_res(g), (uint32_t)p.a_tile_bytes);
+                        tma_load_4d(slot, &p.tm_r, bar_res(g), ch0, w0, h0, n0img);
                     }
                 }
-                named_bar_sync(1, 128);
+                named_bar_sync(1 + g, 128);
                 uint32_t v[32];
                 const uint32_t tbase = tbase0 + (uint32_t)(c * 32);
                 tmem_ld_32x32(tbase, v);
@@ -303,18 +323,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) conv_tcgen05
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(x[j]));
                 }
-                if (c == nlive - 1) {
-                    // last TMEM read of this tile: hand the accumulators back so the next tile's MMAs can start
+                if (c == last_c) {
+                    // this thread's last TMEM read of the tile: hand the accumulators back (256 arrivals release the MMA warp)
                     tc_fence_before();
                     mbar_arrive(bar_tempty(buf));
                 }
-                if (p.res_mode == RES_TILE) mbar_wait(bar_res(sb), (cc >> 1) & 1u);
-                float* stg = reinterpret_cast<float*>(epi_gen + sb * Cfg::A_BYTES + row * 128);
-                const float* up = nullptr;
-                if (p.res_mode == RES_UPSAMPLE2X && row_valid) {
-                    const int uy = min((h0 + ph_) >> 1, p.up_h - 1), ux = min((w0 + pw_) >> 1, p.up_w - 1);
-                    up = p.up_src + (((size_t)(n0img + pn_) * p.up_h + uy) * p.up_w + ux) * (size_t)p.cout + ch0;
-                }
+                if (p.res_mode == RES_TILE) mbar_wait(bar_res(g), gc & 1u);
+                float* stg = reinterpret_cast<float*>(slot_gen + row * 128);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {       // 8 x 16-byte pieces of this row's 128-byte line
                     const int chj = ch0 + j * 4;
@@ -329,13 +344,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) conv_tcgen05
                     o.z = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
                     o.w = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
                     const int pj = j ^ (row & 7);      // SWIZZLE_128B: 16-byte piece index XOR (row mod 8)
-                    float4* slot = reinterpret_cast<float4*>(stg) + pj;
+                    float4* sl = reinterpret_cast<float4*>(stg) + pj;
                     if (p.res_mode == RES_TILE) {
-                        const float4 r = *slot;
+                        const float4 r = *sl;
                         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                    } else if (up != nullptr && chj < p.cout) {
-                        const float4 r = __ldg(reinterpret_cast<const float4*>(up + j * 4));
-                        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                    } else {
+                        o.x += rr[j].x; o.y += rr[j].y; o.z += rr[j].z; o.w += rr[j].w;       // zeros when there is no operand
                     }
                     if (p.relu) {
                         o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
@@ -347,12 +361,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) conv_tcgen05
                         if (chj + 2 < p.sigmoid_ch) o.z = 1.f / (1.f + expf(-o.z));
                         if (chj + 3 < p.sigmoid_ch) o.w = 1.f / (1.f + expf(-o.w));
                     }
-                    *slot = o;
+                    *sl = o;
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(1, 128);
+                named_bar_sync(1 + g, 128);
                 if (et == 0) {
-                    tma_store_4d(&p.tm_d, epi_base + sb * Cfg::A_BYTES, ch0, w0, h0, n0img);
+                    tma_store_4d(&p.tm_d, slot, ch0, w0, h0, n0img);
                     tma_store_commit();
                 }
             }
