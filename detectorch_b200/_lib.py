@@ -16,6 +16,9 @@ SIGNATURES = {
                                               c_void_p, c_void_p]),
     "dt_roi_align_forward_nchw": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
                                           c_void_p, c_void_p]),
+    "dt_roi_align_fast_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
+    "dt_roi_align_forward_nchw_fast": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
+                                               c_void_p, c_void_p, c_void_p]),
     "dt_roi_align_forward_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                           c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dt_nms_workspace_bytes": (c_int64, [c_int64]),

@@ -438,8 +438,12 @@ cudaError_t fn_collect(Engine* e, cudaStream_t s) {
 cudaError_t fn_roi_box(Engine* e, cudaStream_t s) {
     const int R = e->cfg.batch * e->cfg.post_nms_top_n;
     // per-image counts: padded rows carry zero boxes (collect_kernel) -> harmless, fully defined output
-    roi_align_nhwc_kernel<<<R < 148 * 64 ? R : 148 * 64, 256, 0, s>>>(e->roi_lv, e->buf("rois"), e->buf<int>("roi_levels"), nullptr, R, 256, 7, 7,
-                                                                      2, e->buf("roi_feat"));
+    if (e->cfg.exact_roialign)
+        roi_align_nhwc_kernel<<<R < 148 * 64 ? R : 148 * 64, 256, 0, s>>>(e->roi_lv, e->buf("rois"), e->buf<int>("roi_levels"), nullptr, R, 256, 7, 7,
+                                                                          2, e->buf("roi_feat"));
+    else
+        roi_align_fast_nhwc_kernel<<<R < 148 * 64 ? R : 148 * 64, 256, 0, s>>>(e->roi_lv, e->buf("rois"), e->buf<int>("roi_levels"), R, 256, 7, 7,
+                                                                               e->buf("roi_feat"));
     return cudaGetLastError();
 }
 cudaError_t fn_softmax(Engine* e, cudaStream_t s) {
@@ -466,8 +470,12 @@ cudaError_t fn_mask_rois(Engine* e, cudaStream_t s) {
 }
 cudaError_t fn_mask_roi_feat(Engine* e, cudaStream_t s) {
     const int D = e->cfg.batch * e->cfg.det_cap;
-    roi_align_nhwc_kernel<<<D < 148 * 64 ? D : 148 * 64, 256, 0, s>>>(e->roi_lv, e->buf("mask_rois"), e->buf<int>("mask_levels"), nullptr, D, 256, 14,
-                                                                      14, 2, e->buf("mask_feat"));
+    if (e->cfg.exact_roialign)
+        roi_align_nhwc_kernel<<<D < 148 * 64 ? D : 148 * 64, 256, 0, s>>>(e->roi_lv, e->buf("mask_rois"), e->buf<int>("mask_levels"), nullptr, D, 256, 14,
+                                                                          14, 2, e->buf("mask_feat"));
+    else
+        roi_align_fast_nhwc_kernel<<<D < 148 * 64 ? D : 148 * 64, 256, 0, s>>>(e->roi_lv, e->buf("mask_rois"), e->buf<int>("mask_levels"), D, 256, 14, 14,
+                                                                               e->buf("mask_feat"));
     return cudaGetLastError();
 }
 cudaError_t fn_mask_out(Engine* e, cudaStream_t s) {
@@ -645,6 +653,8 @@ bool build_program(Engine* e, std::map<std::string, ConvW>* cw) {
     return pb.ok;
 }
 
+#include "engine_c4.inc"
+
 int load_param(Engine* e, const std::string& name, const float* src, long long numel, cudaStream_t st) {
     auto it = e->params.find(name);
     if (it == e->params.end()) return 2;   // not a hot-path parameter (running stats, fc, duplicates): ignored
@@ -686,7 +696,7 @@ int load_param(Engine* e, const std::string& name, const float* src, long long n
 extern "C" {
 
 dt_engine_t dt_engine_create(const dt_engine_config* cfg) {
-    if (!cfg || cfg->batch < 1 || cfg->height < 32 || cfg->width < 32 || (cfg->height % 32) || (cfg->width % 32)) {
+    if (!cfg || cfg->batch < 1 || cfg->height < 32 || cfg->width < 32 || (cfg->model_type != 1 && ((cfg->height % 32) || (cfg->width % 32)))) {
         fprintf(stderr, "[detectorch_b200] engine: image size must be a multiple of 32 (FPN), batch >= 1\n");
         return nullptr;
     }
@@ -699,8 +709,8 @@ dt_engine_t dt_engine_create(const dt_engine_config* cfg) {
     e->cfg = *cfg;
     if (e->cfg.passes != 1) e->cfg.passes = 3;
     std::map<std::string, ConvW> cw;
-    build_param_table(e, &cw);
-    plan_buffers(e);
+    if (e->cfg.model_type == 1) { build_param_table_c4(e, &cw); plan_buffers_c4(e); }
+    else { e->cfg.use_rpn = 1; build_param_table(e, &cw); plan_buffers(e); }
     return e;
 }
 
@@ -727,9 +737,9 @@ int dt_engine_bind(dt_engine_t h, void* weights, void* workspace, dt_stream_t st
     {   // rebuild the (deterministic) table to recover the ConvW offsets
         Engine tmp;
         tmp.cfg = e->cfg;
-        build_param_table(&tmp, &cw);
+        if (e->cfg.model_type == 1) build_param_table_c4(&tmp, &cw); else build_param_table(&tmp, &cw);
     }
-    if (!build_program(e, &cw)) return 0;
+    if (!(e->cfg.model_type == 1 ? build_program_c4(e, &cw) : build_program(e, &cw))) return 0;
     e->bound = true;
     return 1;
 }

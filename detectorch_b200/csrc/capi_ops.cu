@@ -53,6 +53,59 @@ extern "C" int dt_roi_align_forward_nhwc(const float* const* feats, const int* h
     return 1;
 }
 
+// fast (separable, fused-multiply-add) variants for sampling_ratio == 2 -------------------------------------------------
+namespace {
+__global__ void nchw_to_nhwc_tr_kernel(const float* __restrict__ x, int HW, int C, float* __restrict__ y) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int c = c0 + r, p = p0 + threadIdx.x;
+        tile[r][threadIdx.x] = (p < HW && c < C) ? x[((size_t)b * C + c) * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int p = p0 + r, c = c0 + threadIdx.x;
+        if (c < C && p < HW) y[((size_t)b * HW + p) * C + c] = tile[threadIdx.x][r];
+    }
+}
+}  // namespace
+
+extern "C" int64_t dt_roi_align_fast_workspace_bytes(int batch, int channels, int height, int width) {
+    return (int64_t)batch * channels * height * width * 4;
+}
+
+extern "C" int dt_roi_align_forward_nchw_fast(const float* features, int batch, const float* rois, int64_t num_rois, int roi_cols, int channels,
+                                              int height, int width, int pooled_height, int pooled_width, float spatial_scale,
+                                              int sampling_ratio, float* out, void* workspace, dt_stream_t stream) {
+    if (num_rois <= 0) return 1;
+    // channel slab: the largest divisor of C (multiple of 4) whose [CS][ph*pw] fp32 tile fits ~50 KB of shared memory
+    int cs = 0;
+    for (int d = channels; d >= 4; --d)
+        if (channels % d == 0 && (d & 3) == 0 && (size_t)d * pooled_height * pooled_width * 4 <= 56 * 1024 && ((size_t)d * pooled_height * pooled_width * 4) % 16 == 0) { cs = d; break; }
+    const size_t tile_bytes = (size_t)cs * pooled_height * pooled_width * 4;
+    if (sampling_ratio != 2 || (channels & 3) || pooled_height > kMaxPooled || pooled_width > kMaxPooled || cs == 0) {
+        // outside the fast path's envelope: the exact kernel handles every configuration
+        return dt_roi_align_forward_nchw(features, rois, num_rois, roi_cols, channels, height, width, pooled_height, pooled_width, spatial_scale,
+                                         sampling_ratio, out, stream);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* nhwc = reinterpret_cast<float*>(workspace);
+    const int HW = height * width;
+    nchw_to_nhwc_tr_kernel<<<dim3((HW + 31) / 32, (channels + 31) / 32, batch), dim3(32, 8), 0, st>>>(features, HW, channels, nhwc);
+    DT_CHECK_CUDA(cudaGetLastError());
+    static bool attr_set = false;
+    if (!attr_set) {
+        DT_CHECK_CUDA(cudaFuncSetAttribute(roi_align_fast_nchw_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    const int grid = (int)(num_rois < (int64_t)kNumSMs * 4 ? num_rois : (int64_t)kNumSMs * 4);
+    roi_align_fast_nchw_out_kernel<<<grid, 256, tile_bytes, st>>>(nhwc, rois, (long long)num_rois, roi_cols, channels, cs, height, width, pooled_height,
+                                                                  pooled_width, spatial_scale, out);
+    DT_CHECK_CUDA(cudaGetLastError());
+    return 1;
+}
+
 // ================================================================================== NMS (single set, boxes.nms contract)
 namespace {
 struct NmsWs {

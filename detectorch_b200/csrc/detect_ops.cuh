@@ -131,6 +131,24 @@ static __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int B, i
     }
 }
 
+// global average pool of the res5 head: x [R, S, C] (S = 7*7 positions, NHWC) -> y [R, C]   (torchvision avgpool, detector.py:136,191)
+static __global__ void avgpool_nhwc_kernel(const float* __restrict__ x, int R, int S, int C, float* __restrict__ y) {
+    const int C4 = C >> 2;
+    const long long total = (long long)R * C4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        const long long r = i / C4;
+        const float4* p = reinterpret_cast<const float4*>(x + (size_t)r * S * C) + c4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < S; ++s) {
+            const float4 v = __ldg(p + (size_t)s * C4);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        const float inv = 1.f / (float)S;
+        reinterpret_cast<float4*>(y)[i] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    }
+}
+
 // ---------------------------------------------------------------------------------- box decode helpers
 // generate_proposals.py:165-214 / boxes.py:168-208: separate mul and add (torch / numpy evaluate op by op)
 __device__ __forceinline__ float4 decode_box(float4 box, float dx, float dy, float dw, float dh) {

@@ -10,7 +10,7 @@ from . import _lib
 ARCH_BLOCKS = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3)}
 
 
-def param_table(arch="resnet50", use_mask=True, num_classes=81):
+def param_table(arch="resnet50", use_mask=True, num_classes=81, model="fpn", use_rpn=True):
     """{reference state_dict name: numel} the engine expects (no GPU needed)."""
     L = _lib.lib()
     _bind_engine_api(L)
@@ -19,6 +19,7 @@ def param_table(arch="resnet50", use_mask=True, num_classes=81):
     cfg.batch, cfg.height, cfg.width = 1, 64, 64
     cfg.pre_nms_top_n = cfg.post_nms_top_n = 1000
     cfg.num_classes, cfg.max_dets, cfg.det_cap, cfg.use_mask = num_classes, 100, 100, int(use_mask)
+    cfg.model_type, cfg.use_rpn = (1 if model == "c4" else 0), int(use_rpn)
     h = L.dt_engine_create(ctypes.byref(cfg))
     out = {}
     buf = ctypes.create_string_buffer(256)
@@ -40,7 +41,7 @@ class EngineConfig(ctypes.Structure):
                 ("rpn_min_size", ctypes.c_float), ("num_classes", ctypes.c_int), ("score_thresh", ctypes.c_float),
                 ("det_nms_thresh", ctypes.c_float), ("max_dets", ctypes.c_int), ("det_cap", ctypes.c_int),
                 ("use_mask", ctypes.c_int), ("output_prob", ctypes.c_int), ("emit_full_masks", ctypes.c_int),
-                ("passes", ctypes.c_int), ("precise_mask", ctypes.c_int), ("stem_im2col", ctypes.c_int)]
+                ("passes", ctypes.c_int), ("precise_mask", ctypes.c_int), ("stem_im2col", ctypes.c_int), ("exact_roialign", ctypes.c_int), ("model_type", ctypes.c_int), ("use_rpn", ctypes.c_int)]
 
 
 _DTYPES = {0: torch.float32, 1: torch.int32, 2: torch.uint8}
@@ -72,7 +73,7 @@ def _bind_engine_api(L):
 class Engine:
     def __init__(self, arch="resnet50", batch=1, height=800, width=1216, pre_nms_top_n=1000, post_nms_top_n=1000,
                  rpn_nms_thresh=0.7, rpn_min_size=0.0, num_classes=81, score_thresh=0.05, det_nms_thresh=0.5, max_dets=100,
-                 det_cap=100, use_mask=True, output_prob=True, emit_full_masks=False, passes=3, precise_mask=True, stem_im2col=False, device="cuda:0"):
+                 det_cap=100, use_mask=True, output_prob=True, emit_full_masks=False, passes=3, precise_mask=True, stem_im2col=False, exact_roialign=False, model="fpn", use_rpn=True, device="cuda:0"):
         if not torch.cuda.is_available():
             raise RuntimeError("detectorch_b200.Engine needs a CUDA device (no CPU fallback)")
         self.L = _lib.lib()
@@ -88,6 +89,9 @@ class Engine:
         cfg.use_mask, cfg.output_prob, cfg.emit_full_masks, cfg.passes = int(use_mask), int(output_prob), int(emit_full_masks), passes
         cfg.precise_mask = int(precise_mask)
         cfg.stem_im2col = int(stem_im2col)
+        cfg.exact_roialign = int(exact_roialign)
+        cfg.model_type = 1 if model == "c4" else 0
+        cfg.use_rpn = int(use_rpn)
         self.cfg = cfg
         self.h = self.L.dt_engine_create(ctypes.byref(cfg))
         if not self.h:

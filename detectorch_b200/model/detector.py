@@ -14,7 +14,7 @@ import numpy as np
 import torch
 import torchvision.models as models
 
-from ..engine import Engine, ST_TRUNK, ST_BOX_HEAD, ST_DETECT, ST_MASK_ROI_FEAT, ST_MASK_OUT
+from ..engine import Engine, ST_TRUNK, ST_ROI_BOX, ST_BOX_HEAD, ST_DETECT, ST_MASK_ROI_FEAT, ST_MASK_OUT
 from ..utils import result_utils as _result_utils
 
 
@@ -52,10 +52,11 @@ class _RpnHead(torch.nn.Module):           # detector.py:114-121
 class _MaskHead(torch.nn.Module):
     """mask_head of the reference (detector.py:84-112); forward(x, rois, roi_original_idx) keeps its signature."""
 
-    def __init__(self, owner, output_prob):
+    def __init__(self, owner, output_prob, conv_head=None):
         super().__init__()
-        self.conv_head = _FourConv()
-        self.transposed_conv = torch.nn.ConvTranspose2d(256, 256, 2, stride=2)
+        # '1up4convs': own 4-conv tower; 'upshare': the res5 block shared with the box head (detector.py:217-221)
+        self.conv_head = _FourConv() if conv_head is None else conv_head
+        self.transposed_conv = torch.nn.ConvTranspose2d(256 if conv_head is None else 2048, 256, 2, stride=2)
         self.classif_logits = torch.nn.Conv2d(256, 81, 1)
         self.output_prob = output_prob
         self.roi_height = self.roi_width = 14
@@ -99,26 +100,36 @@ class detector(torch.nn.Module):
         self.use_two_layer_mlp_head = conv_head_layers == 'two_layer_mlp'
         self.output_prob = output_prob
         self.N_classes = N_classes
-        supported = (self.use_fpn_body and self.use_rpn_head and self.use_two_layer_mlp_head and fpn_extra_lvl and
-                     list(fpn_layers) == ['layer1', 'layer2', 'layer3', 'layer4'] and self.roi_height == 7 and self.roi_width == 7 and
-                     self.roi_sampling_ratio == 2 and self.roi_spatial_scale == [0.25, 0.125, 0.0625, 0.03125] and
-                     (not use_mask_head or mask_head_type == '1up4convs') and arch in ('resnet50', 'resnet101') and not train)
-        if not supported:
-            raise NotImplementedError("detectorch_b200 (round 1) implements the FPN+RPN(+1up4convs mask) inference family "
-                                      "(eval_faster_FPN / eval_mask_FPN kwargs); C4 configurations are not built yet")
+        fpn_ok = (self.use_fpn_body and self.use_rpn_head and self.use_two_layer_mlp_head and fpn_extra_lvl and
+                  list(fpn_layers) == ['layer1', 'layer2', 'layer3', 'layer4'] and self.roi_height == 7 and self.roi_width == 7 and
+                  self.roi_sampling_ratio == 2 and self.roi_spatial_scale == [0.25, 0.125, 0.0625, 0.03125] and
+                  (not use_mask_head or mask_head_type == '1up4convs'))
+        c4_ok = (not self.use_fpn_body and list(conv_body_layers) == ['conv1', 'bn1', 'relu', 'maxpool', 'layer1', 'layer2', 'layer3'] and
+                 list(conv_head_layers) == ['layer4', 'avgpool'] and self.roi_height == 14 and self.roi_width == 14 and
+                 self.roi_sampling_ratio == 0 and self.roi_spatial_scale == 0.0625 and (not use_mask_head or mask_head_type == 'upshare'))
+        if not ((fpn_ok or c4_ok) and arch in ('resnet50', 'resnet101') and not train):
+            raise NotImplementedError("detectorch_b200 implements the reference's inference configurations (eval_*.ipynb kwargs): "
+                                      "R-50/101-FPN + RPN (+1up4convs mask) and R-50/101-C4 Fast/Faster/Mask (upshare); got something else")
+        self.family = "fpn" if fpn_ok else "c4"
         if arch.startswith('resnet'):
             self.model = getattr(models, arch)()
         else:
             raise NotImplementedError('Only resnet implemented so far!')
-        self.conv_body = _FpnBody(torch.nn.Sequential(*[getattr(self.model, l) for l in conv_body_layers]), (256, 512, 1024, 2048), fpn_layers)
-        self.conv_head = _TwoLayerMlp()
-        self.rpn = _RpnHead(256, 256, 3)
-        # with the two-layer MLP head the RoI feature is 1024-d (detector.py:143,212 default of 2048 only fits the C4 head)
-        feat = 1024 if self.use_two_layer_mlp_head else roi_feature_channels
+        if self.family == "fpn":
+            self.conv_body = _FpnBody(torch.nn.Sequential(*[getattr(self.model, l) for l in conv_body_layers]), (256, 512, 1024, 2048), fpn_layers)
+            self.conv_head = _TwoLayerMlp()
+            self.rpn = _RpnHead(256, 256, 3)
+            feat = 1024      # two-layer MLP head (detector.py:143,212: the 2048 default only fits the C4 head)
+        else:
+            self.conv_body = torch.nn.Sequential(*[getattr(self.model, l) for l in conv_body_layers])
+            self.conv_head = torch.nn.Sequential(*[getattr(self.model, l) for l in conv_head_layers])
+            if self.use_rpn_head:
+                self.rpn = _RpnHead(1024, 1024, 15)
+            feat = roi_feature_channels
         self.bbox_head = torch.nn.Linear(feat, 4 * N_classes)
         self.classif_head = torch.nn.Linear(feat, N_classes)
         if self.use_mask_head:
-            self.mask_head = _MaskHead(self, output_prob)
+            self.mask_head = _MaskHead(self, output_prob, None if self.family == "fpn" else self.conv_head[0])
         self._engines = {}
         self._engine = None
         self._weights_version = 0
@@ -182,6 +193,8 @@ class detector(torch.nn.Module):
                 raise RuntimeError("detectorch_b200.detector runs on CUDA only: call model.cuda() first (no CPU fallback)")
             kw = dict(arch=self.arch, batch=batch, height=h, width=w, num_classes=self.N_classes, use_mask=self.use_mask_head,
                       output_prob=self.output_prob, emit_full_masks=True, det_cap=128, device=dev)
+            if self.family == "c4":
+                kw.update(model="c4", use_rpn=self.use_rpn_head, pre_nms_top_n=6000, post_nms_top_n=1000, exact_roialign=True)
             kw.update(overrides)
             eng = Engine(**kw)
             eng.load_state_dict(self.state_dict())
@@ -192,27 +205,66 @@ class detector(torch.nn.Module):
     def forward(self, image, rois=None, scaling_factor=None, roi_original_idx=None):
         """-> (cls_score [R,81], bbox_pred [R,324], rois [R,4], img_features [P2..P5])   detector.py:233-286.
         Batch 1 like the reference; `detect()` below is the batched fused path."""
-        if rois is not None:
-            raise NotImplementedError("pre-computed proposals (Fast R-CNN) are not built yet")
         if image.size(0) != 1:
             raise RuntimeError("detector.forward keeps the reference's batch-1 contract; use detector.detect for batches")
         sf = float(scaling_factor.reshape(-1)[0]) if torch.is_tensor(scaling_factor) else float(1.0 if scaling_factor is None else scaling_factor)
-        eng = self.engine_for(1, image.size(2), image.size(3))
-        self._engine = eng
-        self._last_sf = sf
-        _result_utils.set_active_engine(eng)
-        eng.run(image.contiguous().float(), sf, ST_TRUNK, ST_BOX_HEAD)
-        n = int(eng.buffer("roi_counts")[0].item())
+        image = image.contiguous().float()
+        if self.family == "fpn":
+            if rois is not None:
+                raise NotImplementedError("pre-computed proposals with the FPN body (eval_fast_FPN) are not built yet")
+            eng = self.engine_for(1, image.size(2), image.size(3))
+            self._activate(eng, sf)
+            eng.run(image, sf, ST_TRUNK, ST_BOX_HEAD)
+            n = int(eng.buffer("roi_counts")[0].item())
+            feats = [eng.buffer("P%d" % l).permute(0, 3, 1, 2) for l in (2, 3, 4, 5)]     # NCHW-shaped views of the NHWC maps
+        else:
+            if self.use_rpn_head:
+                eng = self.engine_for(1, image.size(2), image.size(3))
+                self._activate(eng, sf)
+                eng.run(image, sf, ST_TRUNK, ST_BOX_HEAD)
+                n = int(eng.buffer("roi_counts")[0].item())
+            else:
+                if rois is None:
+                    raise RuntimeError("Fast R-CNN needs pre-computed proposals (eval_fast.ipynb passes batch['rois'])")
+                r = rois.reshape(-1, rois.shape[-1])[:, -4:].float()
+                n = r.size(0)
+                cap = min(1000, max(100, (n + 99) // 100 * 100))
+                if n > cap:
+                    raise RuntimeError("at most 1000 proposals per image are supported")
+                eng = self.engine_for(1, image.size(2), image.size(3), post_nms_top_n=cap)
+                self._activate(eng, sf)
+                eng.run(image, sf, ST_TRUNK, ST_TRUNK)
+                er = eng.buffer("rois")
+                er.zero_()
+                er[0, :n, 1:5] = r.to(eng.device)
+                eng.buffer("roi_counts")[0] = n
+                eng.run(None, sf, ST_ROI_BOX, ST_BOX_HEAD)
+            feats = eng.buffer("C4").permute(0, 3, 1, 2)
         cls_score = eng.buffer("cls_prob")[:n]
         bbox_pred = eng.buffer("bbox_pred")[:n]
         out_rois = eng.buffer("rois")[0, :n, 1:5]
-        feats = [eng.buffer("P%d" % l).permute(0, 3, 1, 2) for l in (2, 3, 4, 5)]     # NCHW-shaped views of the NHWC maps
         return (cls_score, bbox_pred, out_rois, feats)
+
+    def _activate(self, eng, sf):
+        self._engine = eng
+        self._last_sf = sf
+        _result_utils.set_active_engine(eng)
 
     def _run_mask_head(self, img_features, rois, roi_original_idx):
         eng = self._engine
         if eng is None:
             raise RuntimeError("mask_head called before forward")
+        if self.family == "c4":
+            r = rois if torch.is_tensor(rois) else torch.cat(tuple(rois), 0)
+            r = r.reshape(-1, r.shape[-1])[:, -4:].to(eng.device).float()        # detector.py:100-101 (preprocess_rois)
+            n = r.size(0)
+            mr = eng.buffer("mask_rois")
+            if n > mr.size(0):
+                raise RuntimeError("mask_head: %d RoIs exceed the engine capacity %d" % (n, mr.size(0)))
+            mr.zero_()
+            mr[:n, 1:5] = r
+            eng.run(None, self._last_sf, ST_MASK_ROI_FEAT, ST_MASK_OUT)
+            return eng.buffer("masks_full")[:n]
         # per-level lists -> original order (detector.py:103-106)
         lv, parts = [], []
         for i, r in enumerate(rois):

@@ -42,6 +42,24 @@ def roi_align_forward_nchw(features, rois, pooled_height, pooled_width, spatial_
     return out
 
 
+def roi_align_forward_nchw_fast(features, rois, pooled_height, pooled_width, spatial_scale, sampling_ratio, out=None):
+    """Same contract as roi_align_forward_nchw; sampling_ratio == 2 takes the separable / FMA fast path (fp32 re-association
+    differences only), anything else is forwarded to the exact kernel."""
+    _need_cuda(features, rois)
+    if not (features.is_contiguous() and rois.is_contiguous()):
+        raise RuntimeError("roi_align: features and rois must be contiguous")
+    B, C, H, W = features.shape
+    R = rois.size(0)
+    if out is None:
+        out = torch.empty((R, C, pooled_height, pooled_width), device=features.device, dtype=torch.float32)
+    L = _lib.lib()
+    ws = torch.empty((L.dt_roi_align_fast_workspace_bytes(B, C, H, W),), dtype=torch.uint8, device=features.device)
+    ok = L.dt_roi_align_forward_nchw_fast(_p(features), B, _p(rois), R, rois.size(1), C, H, W, int(pooled_height), int(pooled_width),
+                                          float(spatial_scale), int(sampling_ratio), _p(out), _p(ws), _stream())
+    _lib.check(ok, "dt_roi_align_forward_nchw_fast")
+    return out
+
+
 def roi_align_forward_nhwc(feats, scales, rois, level, pooled_height, pooled_width, sampling_ratio, num_rois=None):
     """feats: list of NHWC maps [B,H,W,C]; rois [R,5]; level int32 [R] or None -> out [R,ph,pw,C]."""
     _need_cuda(rois, *feats)

@@ -40,6 +40,16 @@ int dt_roi_align_forward_nchw(const float* features, const float* rois, int64_t 
                               int width, int pooled_height, int pooled_width, float spatial_scale, int sampling_ratio, float* out,
                               dt_stream_t stream);
 
+/* Fast variant for sampling_ratio == 2 (the FPN configurations and the RoIAlign microbench): separable bilinear weights with
+ * merged duplicate taps, fused multiply-adds, output tile assembled in shared memory and written by one bulk async copy per
+ * RoI.  Same contract as dt_roi_align_forward_nchw (any other configuration is forwarded to it); results agree with the
+ * exact kernel to fp32 re-association (~1e-7 relative).  workspace: dt_roi_align_fast_workspace_bytes() (an NHWC copy of
+ * the feature map). */
+int64_t dt_roi_align_fast_workspace_bytes(int batch, int channels, int height, int width);
+int dt_roi_align_forward_nchw_fast(const float* features, int batch, const float* rois, int64_t num_rois, int roi_cols, int channels, int height,
+                                   int width, int pooled_height, int pooled_width, float spatial_scale, int sampling_ratio, float* out,
+                                   void* workspace, dt_stream_t stream);
+
 /* Multi-level NHWC variant used inside the fused detector (replaces the 4 per-level RoIAlign calls + cat +
  * index-restore of lib/model/detector.py:259-270 and :100-106).  feats[l] is an NHWC map [B,H[l],W[l],C];
  * rois [max_rois,5]; level[max_rois] (index into feats, NULL = all level 0); num_rois_dev: optional device int
@@ -100,6 +110,10 @@ typedef struct dt_engine_config {
     int passes;                  /* 3 = 3xTF32 (fp32-accurate, default), 1 = single-pass TF32 */
     int precise_mask;            /* 1 = mask-head convs use 128-wide tiles with 3 rotating accumulators (tighter fp32 parity) */
     int stem_im2col;             /* 1 = force the im2col + GEMM stem instead of the fused TMA-window stem (debug) */
+    int exact_roialign;          /* 1 = RoIAlign in the reference's exact fp32 operation order (bit-identical to its CPU loop);
+                                    0 = separable / FMA fast path (fp32 re-association only, ~1e-7 relative) */
+    int model_type;              /* 0 = R-50/101-FPN + RPN (+ '1up4convs' mask head); 1 = R-50/101-C4 (res5 head, 'upshare' mask head) */
+    int use_rpn;                 /* C4 only: 1 = Faster/Mask R-CNN (single-level RPN), 0 = Fast R-CNN (caller fills the `rois` buffer) */
 } dt_engine_config;
 
 typedef void* dt_engine_t;

@@ -113,6 +113,20 @@ _STD_MULT = [
 ]
 
 
+# the C4 heads see different feature statistics (1024-ch C4 map, 2048-d pooled res5 features): own multipliers
+_STD_MULT_C4 = [
+    ("model.conv1.weight", 1.0 / 50.0),
+    ("downsample.0", 0.7),
+    ("rpn.conv_rpn", 0.35),
+    ("rpn.rpn_cls_prob", 1.0),
+    ("rpn.rpn_bbox_pred", 0.06),
+    ("bbox_head", 0.12),
+    ("classif_head", 0.6),
+    ("mask_head.transposed_conv", 0.5),
+    ("mask_head.classif_logits", 1.0),
+]
+
+
 def synthetic_params(arch="resnet50", fpn=True, rpn=True, mask=True, seed=0, n_classes=81):
     """Deterministic synthetic weights: per-parameter generator seeded by
     crc32(name)^seed, He-style conv scale, BN gains chosen so activations stay O(1-10),
@@ -134,7 +148,7 @@ def synthetic_params(arch="resnet50", fpn=True, rpn=True, mask=True, seed=0, n_c
             if name == "mask_head.transposed_conv.weight":
                 fan_in = shape[0]      # ConvTranspose2d weight is [Cin, Cout, kh, kw], stride==kernel
             std = (2.0 / fan_in) ** 0.5
-            for pat, mult in _STD_MULT:
+            for pat, mult in (_STD_MULT if fpn else _STD_MULT_C4):
                 if pat in name:
                     std *= mult
                     break
@@ -291,4 +305,64 @@ def detect_and_mask_fpn(image, P, arch="resnet50", scaling_factor=1.0, **kw):
         with torch.no_grad():
             S["masks"], S["mask_logits"], S["mask_roi_feats"] = mask_head_fpn(S["P"], per_level, idx.astype(np.int64), P,
                                                                               True, return_logits=True)
+    return S
+
+
+# ----------------------------------------------------------------------------- C4 model family
+C4_ANCHOR_SIZES = (32, 64, 128, 256, 512)
+
+
+def res5_head(x, P, arch="resnet50"):
+    """conv_head = [layer4, avgpool] run per RoI (detector.py:136,191,273): [R,1024,14,14] -> ([R,2048], [R,2048,7,7])."""
+    y = layer(x, P, arch, 4)
+    return F.adaptive_avg_pool2d(y, (1, 1)).view(y.size(0), -1), y
+
+
+def forward_c4(image, P, arch="resnet50", proposals=None, scaling_factor=1.0, pre_nms=6000, post_nms=1000, output_prob=True):
+    """detector.forward for the C4 configurations, batch 1 (detector.py:233-286): Fast R-CNN when `proposals` [R,4] is given
+    (eval_fast.ipynb), Faster R-CNN otherwise (single-level RPN, eval_faster.ipynb)."""
+    assert image.size(0) == 1
+    h, w = image.size(2), image.size(3)
+    S = {}
+    with torch.no_grad():
+        S["C4"] = trunk(image, P, arch, 3)[-1]
+        if proposals is None:
+            S["rpn"] = rpn_head(S["C4"], P)
+            pr, sc, st = ref.generate_proposals_level(S["rpn"][0], S["rpn"][1], h, w, scaling_factor, 0.0625, C4_ANCHOR_SIZES,
+                                                      pre_nms_top_n=pre_nms, post_nms_top_n=post_nms, return_stages=True)
+            S["props"] = (pr, sc, st)
+            rois = pr
+        else:
+            rois = torch.as_tensor(proposals, dtype=torch.float32)
+        S["rois"] = rois
+        feats = torch.from_numpy(ref.roi_align_forward(S["C4"].numpy(), rois.numpy(), 14, 14, 0.0625, 0))
+        S["roi_feats"] = feats
+        pooled, S["res5"] = res5_head(feats, P, arch)
+        S["pooled"] = pooled
+        cls = F.linear(pooled, P["classif_head.weight"], P["classif_head.bias"])
+        S["cls_logits"] = cls
+        S["cls_score"] = F.softmax(cls, dim=1) if output_prob else cls
+        S["bbox_pred"] = F.linear(pooled, P["bbox_head.weight"], P["bbox_head.bias"])
+    return S
+
+
+def mask_head_c4(c4_feat, rois, P, arch="resnet50", output_prob=True):
+    """mask_head 'upshare' (detector.py:84-112, 217-218): RoIAlign 14x14 sr=0 -> layer4 -> deconv 2x2 s2 + ReLU -> 1x1 -> 81."""
+    with torch.no_grad():
+        x = torch.from_numpy(ref.roi_align_forward(c4_feat.numpy(), np.asarray(rois, dtype=np.float32), 14, 14, 0.0625, 0))
+        roi_feat = x
+        x = layer(x, P, arch, 4)
+        x = F.relu(F.conv_transpose2d(x, P["mask_head.transposed_conv.weight"], P["mask_head.transposed_conv.bias"], stride=2))
+        logits = F.conv2d(x, P["mask_head.classif_logits.weight"], P["mask_head.classif_logits.bias"])
+    return (torch.sigmoid(logits) if output_prob else logits), logits, roi_feat
+
+
+def detect_and_mask_c4(image, P, arch="resnet50", proposals=None, scaling_factor=1.0, use_mask=True, **kw):
+    S = forward_c4(image, P, arch, proposals, scaling_factor, **kw)
+    h, w = image.size(2), image.size(3)
+    im_size = np.array([h / scaling_factor, w / scaling_factor], dtype=np.float32)
+    sf, bf, cb = ref.postprocess_output(S["rois"], scaling_factor, im_size, S["cls_score"], S["bbox_pred"])
+    S["scores_final"], S["boxes_final"], S["cls_boxes"] = sf, bf, cb
+    if use_mask and len(bf):
+        S["masks"], S["mask_logits"], S["mask_roi_feats"] = mask_head_c4(S["C4"], (bf * scaling_factor).astype(np.float32), P, arch)
     return S

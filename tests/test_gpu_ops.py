@@ -71,6 +71,24 @@ def test_roi_align_random_vs_oracle_and_layouts(dev):
     assert ops.roi_align_forward_nchw(torch.from_numpy(f).to(dev), torch.zeros((0, 5), device=dev), 7, 7, 1 / 16., 2).shape == (0, 32, 7, 7)
 
 
+def test_roi_align_fast_path_matches_exact(dev, G):
+    """The separable / FMA fast kernel (sampling_ratio 2) agrees with the bit-exact kernel within fp32 re-association;
+    other sampling ratios are forwarded to the exact kernel."""
+    from detectorch_b200 import ops
+    rng = np.random.RandomState(11)
+    f = torch.from_numpy(rng.randn(2, 64, 50, 68).astype(np.float32)).to(dev)
+    r = np.hstack([rng.randint(0, 2, (3000, 1)).astype(np.float32), _boxes(rng, 3000, 1088, 800)])
+    r[:4, 1:] = [[-100, -100, -50, -50], [5, 5, 5, 5], [0, 0, 1087, 799], [1080, 790, 1200, 900]]
+    r = torch.from_numpy(r).to(dev)
+    for p in (7, 14):
+        exact = ops.roi_align_forward_nchw(f, r, p, p, 1 / 16., 2)
+        fast = ops.roi_align_forward_nchw_fast(f, r, p, p, 1 / 16., 2)
+        assert float((exact - fast).abs().max()) < 2e-5
+    assert torch.equal(ops.roi_align_forward_nchw_fast(f, r, 14, 14, 1 / 16., 0), ops.roi_align_forward_nchw(f, r, 14, 14, 1 / 16., 0))
+    gf, gr = torch.from_numpy(G["roi_feat"]).to(dev), torch.from_numpy(G["roi_rois"]).to(dev)
+    assert np.abs(ops.roi_align_forward_nchw_fast(gf[:, :4].contiguous(), gr, 7, 7, 1 / 16., 2).cpu().numpy() - G["roi_out_p7_sr2_s16"][:, :4]).max() < 1e-5
+
+
 def test_roi_align_mirror_module_and_errors(dev):
     from detectorch_b200.model.roi_align import RoIAlign, RoIAlignFunction
     from oracle import ref
