@@ -221,7 +221,7 @@ def run_ours(args):
         all_ms = sum(m for (m, _, _, _) in prof)
         tf32_peak = bf16_peak / 2.0          # kind::tf32 issues at half the kind::f16 rate (B200_PROFILING.md nominal 1.1 vs 2.25 PF)
         ach = conv_flops / (conv_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "conv_tcgen05_kernel (85 launches/step)", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
+        roof = {"bound": "tensor", "kernel": "conv_tcgen05_kernel (%d launches/step)" % len(conv), "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
                 "frac": ach / tf32_peak, "traffic": None,
                 "peak_source": "%s bf16_tflops_sustained/2 (tf32 MMA rate is half of bf16)" % which,
                 "executed_tflops": 3.0 * ach, "frac_executed": 3.0 * ach / tf32_peak,
@@ -261,7 +261,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
