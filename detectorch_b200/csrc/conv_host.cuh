@@ -2,6 +2,7 @@
 // tile-geometry selection and launch.  No torch types; raw device pointers only.
 #pragma once
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "conv_tcgen05.cuh"
@@ -72,6 +73,7 @@ struct ConvLayer {
     ConvParams p;
     int block_n;
     int nmain = 1;      // rotating main-term accumulators (3 = precise: shorter truncating accumulation chains)
+    bool two_sm = true; // cta_group::2 MMA (default) vs 1-SM MMA + multicast (DT_CONV_1SM=1)
     dim3 grid;
     bool valid = false;
 };
@@ -111,6 +113,20 @@ inline void choose_box(int Wo, int Ho, int N, int max_w, int* wbox, int* hbox, i
     *wbox = bw; *hbox = bh; *nbox = bn;
 }
 
+// MMA mode per layer.  cta_group::2 (each SM keeps half of the weight tile, 3 instead of 2 TMA stages) measured 3-10 % faster on
+// the long-K, 256-wide layers and 15-55 % slower on the short-K / narrow ones (extra cluster-scope barrier traffic per k-block),
+// so it is used only where it wins.  DT_CONV_MMA=1sm|2sm forces one mode everywhere (tests exercise both).
+inline bool conv_use_two_sm(int block_n, int num_kb) {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DT_CONV_MMA");
+        v = (e && e[0] == '1') ? 1 : ((e && e[0] == '2') ? 2 : 0);
+    }
+    if (v == 1) return false;
+    if (v == 2) return true;
+    return block_n == 256 && num_kb >= 32;
+}
+
 // Persistent launch geometry: work items = (pairs of M-tiles) x (N-tiles); one 2-CTA cluster per SM pair (74 on B200),
 // each looping over items pair, pair + num_pairs, ...  An odd M-tile count gets one all-out-of-range surplus tile (TMA
 // zero-fills its loads and clips its stores) so that both CTAs of a pair always run the same multicast protocol.
@@ -121,6 +137,7 @@ inline void finish_grid(ConvLayer* L, int n_tiles) {
     p.n_tiles = n_tiles;
     const int items = p.m_pairs * p.n_tiles;
     const int pairs = items < kNumSMs / 2 ? items : kNumSMs / 2;
+    L->two_sm = conv_use_two_sm(L->block_n, p.kh * p.kw * p.cin_blocks);
     L->grid = dim3((unsigned)(2 * pairs), 1, 1);
     L->valid = true;
 }
@@ -209,26 +226,31 @@ inline bool conv_build_stem(const float* x4, int B, int Hp, int Wp, int H1, int 
     return true;
 }
 
-template <int BN, int NM>
+template <int BN, int NM, bool TWO>
 inline cudaError_t conv_launch_cfg(const ConvLayer& L, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel<BN, NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN, NM>::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel<BN, NM, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN, NM, TWO>::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    conv_tcgen05_kernel<BN, NM><<<L.grid, ConvCfg<BN, NM>::THREADS, ConvCfg<BN, NM>::SMEM_BYTES, stream>>>(L.p);
+    conv_tcgen05_kernel<BN, NM, TWO><<<L.grid, ConvCfg<BN, NM, TWO>::THREADS, ConvCfg<BN, NM, TWO>::SMEM_BYTES, stream>>>(L.p);
     return cudaGetLastError();
+}
+
+template <bool TWO>
+inline cudaError_t conv_launch_sm(const ConvLayer& L, cudaStream_t stream) {
+    switch (L.block_n) {
+        case 64: return conv_launch_cfg<64, 3, TWO>(L, stream);
+        case 128: return L.nmain == 3 ? conv_launch_cfg<128, 3, TWO>(L, stream) : conv_launch_cfg<128, 1, TWO>(L, stream);
+        case 256: return conv_launch_cfg<256, 1, TWO>(L, stream);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 inline cudaError_t conv_launch(const ConvLayer& L, cudaStream_t stream) {
     if (!L.valid) return cudaErrorInvalidValue;
-    switch (L.block_n) {
-        case 64: return conv_launch_cfg<64, 3>(L, stream);
-        case 128: return L.nmain == 3 ? conv_launch_cfg<128, 3>(L, stream) : conv_launch_cfg<128, 1>(L, stream);
-        case 256: return conv_launch_cfg<256, 1>(L, stream);
-        default: return cudaErrorInvalidValue;
-    }
+    return L.two_sm ? conv_launch_sm<true>(L, stream) : conv_launch_sm<false>(L, stream);
 }
 
 }  // namespace dt

@@ -64,15 +64,17 @@ struct ConvParams {
     int passes;            // 3 = 3xTF32 (default), 1 = single TF32
 };
 
-template <int BLOCK_N, int NMAIN>
+template <int BLOCK_N, int NMAIN, bool kTwoSM>
 struct ConvCfg {
     static constexpr int BLOCK_M = 128;
     static constexpr int BLOCK_K = 32;
     static constexpr int A_BYTES = BLOCK_M * 128;                    // 16 KB
-    static constexpr int B_BYTES = BLOCK_N * 128;
+    // 1-SM MMA: every CTA holds the whole BLOCK_N-row weight tile (its half arrives by multicast from the peer).
+    // 2-SM MMA (cta_group::2): every CTA holds only ITS half -> smaller stages, deeper pipeline, half the operand ingest per SM.
+    static constexpr int B_BYTES = (kTwoSM ? BLOCK_N / 2 : BLOCK_N) * 128;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;    // A, A_lo, B_hi, B_lo
-    static constexpr int STAGES = (BLOCK_N == 256) ? 2 : (BLOCK_N == 128 ? 3 : 4);
-    static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;          // 192 KB in all three configurations
+    static constexpr int STAGES = kTwoSM ? (BLOCK_N == 256 ? 3 : 4) : ((BLOCK_N == 256) ? 2 : (BLOCK_N == 128 ? 3 : 4));
+    static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
     static constexpr int EPI_BYTES = 2 * A_BYTES;                    // 2 x (128 rows x 32 channels) staging ring
     static constexpr int TILE_COLS = (NMAIN + 1) * BLOCK_N;          // TMEM columns of one tile's accumulators
     static constexpr int NBUF = (2 * TILE_COLS <= 512) ? 2 : 1;      // double-buffer the accumulators when they fit
@@ -85,9 +87,9 @@ struct ConvCfg {
     static_assert(8 * (NUM_BARS + 1) <= 256, "barrier area");
 };
 
-template <int BLOCK_N, int NMAIN>
+template <int BLOCK_N, int NMAIN, bool kTwoSM>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
-    using Cfg = ConvCfg<BLOCK_N, NMAIN>;
+    using Cfg = ConvCfg<BLOCK_N, NMAIN, kTwoSM>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int NBUF = Cfg::NBUF;
     extern __shared__ uint8_t smem_raw[];
@@ -122,18 +124,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
         if (p.res_mode == RES_TILE) tma_prefetch_desc(&p.tm_r);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full(s), 1);
-            mbar_init(bar_conv(s), 128);
-            mbar_init(bar_empty(s), 2);      // own MMA commit + the peer CTA's (its multicast writes land in our stage too)
+            mbar_init(bar_conv(s), kTwoSM ? 256 : 128);     // 2-SM: the leader's issuer also waits for the peer's converters
+            mbar_init(bar_empty(s), kTwoSM ? 1 : 2);        // 1-SM: own MMA commit + the peer's (its multicast writes land in our stage too)
         }
         for (int b = 0; b < NBUF; ++b) {
             mbar_init(bar_tfull(b), 1);
-            mbar_init(bar_tempty(b), 256);
+            mbar_init(bar_tempty(b), kTwoSM ? 512 : 256);   // 2-SM: both CTAs' epilogues release the leader's issuer
         }
         mbar_init(bar_res(0), 1);
         mbar_init(bar_res(1), 1);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    if (warp == 1) {
+        if constexpr (kTwoSM) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot); else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();          // the peer's barriers must be initialised before any multicast / remote arrive
@@ -168,29 +172,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
                     const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
                     mbar_arrive_expect_tx(bar_full(s), tx_bytes);
                     tma_load_4d(st, &p.tm_a, bar_full(s), cb * 32, w0 * p.stride_w + fx - p.pad_w, h0 * p.stride_h + fy - p.pad_h, n0img);
-                    // this CTA's half of the weight rows, multicast to both CTAs of the pair
-                    const uint32_t half = cta_rank * (Cfg::B_BYTES / 2);
+                    // this CTA's half of the weight rows
                     const int nrow = n0 + (int)cta_rank * (BLOCK_N / 2);
-                    tma_load_2d_mcast(st + 2 * Cfg::A_BYTES + half, &p.tm_bhi, bar_full(s), kb * 32, nrow, (uint16_t)3);
-                    if (p.passes == 3)
-                        tma_load_2d_mcast(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + half, &p.tm_blo, bar_full(s), kb * 32, nrow, (uint16_t)3);
+                    if constexpr (kTwoSM) {
+                        // 2-SM MMA: the half stays local (the pair's tensor cores read both halves in place)
+                        tma_load_2d(st + 2 * Cfg::A_BYTES, &p.tm_bhi, bar_full(s), kb * 32, nrow);
+                        if (p.passes == 3) tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &p.tm_blo, bar_full(s), kb * 32, nrow);
+                    } else {
+                        // 1-SM MMA: multicast to both CTAs of the pair
+                        const uint32_t half = cta_rank * (Cfg::B_BYTES / 2);
+                        tma_load_2d_mcast(st + 2 * Cfg::A_BYTES + half, &p.tm_bhi, bar_full(s), kb * 32, nrow, (uint16_t)3);
+                        if (p.passes == 3)
+                            tma_load_2d_mcast(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + half, &p.tm_blo, bar_full(s), kb * 32, nrow, (uint16_t)3);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================================================================ MMA issuer (one elected lane)
-        constexpr uint32_t idesc = umma_idesc(2, 128, BLOCK_N);
+        // ================================================================ MMA issuer (one elected lane; 2-SM: leader CTA only)
+        constexpr uint32_t idesc = umma_idesc(2, kTwoSM ? 256 : 128, BLOCK_N);
         uint32_t it = 0;
         int t = 0;
-        for (int item = pair; item < num_items; item += num_pairs, ++t) {
+        for (int item = pair; item < num_items && (!kTwoSM || cta_rank == 0); item += num_pairs, ++t) {
             const int buf = t % NBUF;
-            mbar_wait(bar_tempty(buf), (((uint32_t)(t / NBUF)) & 1u) ^ 1u);     // the epilogue drained this accumulator set
+            if constexpr (kTwoSM) mbar_wait_cluster(bar_tempty(buf), (((uint32_t)(t / NBUF)) & 1u) ^ 1u);
+            else mbar_wait(bar_tempty(buf), (((uint32_t)(t / NBUF)) & 1u) ^ 1u);     // the epilogue drained this accumulator set
             tc_fence_after();
             const uint32_t acc0 = tmem_acc + (uint32_t)(buf * Cfg::TILE_COLS);
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
-                mbar_wait(bar_conv(s), ph);      // converters waited on full[s] and published A_lo
+                if constexpr (kTwoSM) mbar_wait_cluster(bar_conv(s), ph);   // both CTAs' TMA data landed and both A_lo tiles are published
+                else mbar_wait(bar_conv(s), ph);      // converters waited on full[s] and published A_lo
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
@@ -207,15 +220,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
                         //  * the main term rotates over NMAIN accumulators by k-block (summed with RN adds in the epilogue).
                         const uint32_t acc_main = acc0 + (uint32_t)((kb % NMAIN) * BLOCK_N);
                         const uint32_t main_flag = (kb >= NMAIN || k != 0) ? 1u : 0u;
-                        if (p.passes == 3) {
-                            const uint32_t acc_x = acc0 + (uint32_t)(NMAIN * BLOCK_N);
-                            umma_tf32(acc_x, dal + koff, dbh + koff, idesc, (kb | k) != 0);
-                            umma_tf32(acc_x, da + koff, dbl + koff, idesc, 1u);
+                        if constexpr (kTwoSM) {
+                            if (p.passes == 3) {
+                                const uint32_t acc_x = acc0 + (uint32_t)(NMAIN * BLOCK_N);
+                                umma_tf32_2sm(acc_x, dal + koff, dbh + koff, idesc, (kb | k) != 0);
+                                umma_tf32_2sm(acc_x, da + koff, dbl + koff, idesc, 1u);
+                            }
+                            umma_tf32_2sm(acc_main, da + koff, dbh + koff, idesc, main_flag);
+                        } else {
+                            if (p.passes == 3) {
+                                const uint32_t acc_x = acc0 + (uint32_t)(NMAIN * BLOCK_N);
+                                umma_tf32(acc_x, dal + koff, dbh + koff, idesc, (kb | k) != 0);
+                                umma_tf32(acc_x, da + koff, dbl + koff, idesc, 1u);
+                            }
+                            umma_tf32(acc_main, da + koff, dbh + koff, idesc, main_flag);
                         }
-                        umma_tf32(acc_main, da + koff, dbh + koff, idesc, main_flag);
                     }
-                    umma_commit_mcast(bar_empty(s), (uint16_t)3);       // frees this stage in BOTH CTAs' producers when these MMAs retire
-                    if (kb == num_kb - 1) umma_commit(bar_tfull(buf));  // this tile's accumulators are complete
+                    if constexpr (kTwoSM) {
+                        umma_commit_2sm_mcast(bar_empty(s), (uint16_t)3);                        // frees this stage in both CTAs
+                        if (kb == num_kb - 1) umma_commit_2sm_mcast(bar_tfull(buf), (uint16_t)3);  // both CTAs' accumulators are complete
+                    } else {
+                        umma_commit_mcast(bar_empty(s), (uint16_t)3);       // frees this stage in BOTH CTAs' producers when these MMAs retire
+                        if (kb == num_kb - 1) umma_commit(bar_tfull(buf));  // this tile's accumulators are complete
+                    }
                 }
                 __syncwarp();
             }
@@ -245,7 +272,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
                     }
                     fence_proxy_async_smem();    // generic-proxy writes -> visible to the tensor core (async proxy)
                 }
-                mbar_arrive(bar_conv(s));
+                if constexpr (kTwoSM) mbar_arrive_cluster(mapa_cluster(bar_conv(s), 0));   // the leader CTA's issuer collects both CTAs
+                else mbar_arrive(bar_conv(s));
             }
         }
     } else {
@@ -283,7 +311,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
             const uint32_t tbase0 = tmem_acc + (uint32_t)(buf * Cfg::TILE_COLS) + ((uint32_t)(q * 32) << 16);
             int last_c = -1;                             // this group's last live chunk of the tile
             for (int c = g; c < nlive; c += 2) last_c = c;
-            if (last_c < 0) { tc_fence_before(); mbar_arrive(bar_tempty(buf)); }
+            if (last_c < 0) {
+                tc_fence_before();
+                if constexpr (kTwoSM) mbar_arrive_cluster(mapa_cluster(bar_tempty(buf), 0)); else mbar_arrive(bar_tempty(buf));
+            }
 #pragma unroll 1
             for (int c = g; c < nlive; c += 2, ++gc) {
                 const int ch0 = n0 + c * 32;
@@ -326,7 +357,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
                 if (c == last_c) {
                     // this thread's last TMEM read of the tile: hand the accumulators back (256 arrivals release the MMA warp)
                     tc_fence_before();
-                    mbar_arrive(bar_tempty(buf));
+                    if constexpr (kTwoSM) mbar_arrive_cluster(mapa_cluster(bar_tempty(buf), 0)); else mbar_arrive(bar_tempty(buf));
                 }
                 if (p.res_mode == RES_TILE) mbar_wait(bar_res(g), gc & 1u);
                 float* stg = reinterpret_cast<float*>(slot_gen + row * 128);
@@ -378,7 +409,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
-    if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_acc);
+    if (warp == 1) {
+        if constexpr (kTwoSM) tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_acc); else tmem_dealloc<Cfg::TMEM_COLS>(tmem_acc);
+    }
 }
 
 }  // namespace dt
