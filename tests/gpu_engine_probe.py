@@ -193,6 +193,27 @@ if __name__ == "__main__":
     mode = sys.argv[1]
     if mode == "parity":
         parity()
+    elif mode == "c4":
+        # BASELINE configs[1]: Faster R-CNN R-50-C4, batch 1, 1000 RPN proposals (plus the 'upshare' mask head)
+        P = net.synthetic_params("resnet50", fpn=False)
+        eng = E.Engine(arch="resnet50", model="c4", batch=1, height=800, width=1216, pre_nms_top_n=6000, post_nms_top_n=1000)
+        eng.load_state_dict(P)
+        img = net.synthetic_image(1, 800, 1216).to(dev)
+        for _ in range(3):
+            eng.run(img, 1.0)
+        torch.cuda.synchronize()
+        for (a, b, tag) in ((0, 7, "faster_rcnn_c4 (trunk..detect)"), (0, 11, "mask_rcnn_c4 (trunk..masks)")):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                eng.run(img, 1.0, a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            print("C4 %-34s batch 1: %.3f ms/img -> %.1f img/s; rois %s dets %s" % (tag, ms, 1000.0 / ms, eng.buffer("roi_counts").cpu().tolist(), eng.buffer("det_counts").cpu().tolist()), flush=True)
+        pr = eng.profile(img, 1.0)
+        fl = sum(f for (_, f, _, _) in pr); tm = sum(m for (m, f, _, bn) in pr if bn > 0)
+        print("C4 conv launches: %.1f GFLOP algorithmic in %.3f ms = %.1f TFLOP/s" % (fl / 1e9, tm, fl / tm / 1e9), flush=True)
     elif mode == "ops":
         ops()
     elif mode == "ops_im2col":
