@@ -255,7 +255,17 @@ static __global__ void __launch_bounds__(1024) rpn_proposals_kernel(const __grid
         __shared__ uint32_t sel[4];     // b1, c1, b2, count
         for (int i = threadIdx.x; i < 4096; i += blockDim.x) hist[i] = 0;
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&h1[k0[i] >> 21], 1u);
+        // objectness scores cluster in a few exponent bins: aggregate equal digits inside the warp before touching shared memory
+        for (int base_i = 0; base_i < n; base_i += blockDim.x) {
+            const int i = base_i + threadIdx.x;
+            const bool valid = i < n;
+            const unsigned act = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const uint32_t d = k0[i] >> 21;
+                const unsigned m = __match_any_sync(act, d);
+                if ((m & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&h1[d], (uint32_t)__popc(m));
+            }
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
             uint32_t c = 0, b = 0;
@@ -264,7 +274,17 @@ static __global__ void __launch_bounds__(1024) rpn_proposals_kernel(const __grid
         }
         __syncthreads();
         const uint32_t b1 = sel[0], c1 = sel[1];
-        for (int i = threadIdx.x; i < n; i += blockDim.x) { const uint32_t k = k0[i]; if ((k >> 21) == b1) atomicAdd(&h2[(k >> 10) & 2047u], 1u); }
+        for (int base_i = 0; base_i < n; base_i += blockDim.x) {
+            const int i = base_i + threadIdx.x;
+            const uint32_t k = i < n ? k0[i] : 0u;
+            const bool valid = (i < n) && ((k >> 21) == b1);
+            const unsigned act = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const uint32_t d = (k >> 10) & 2047u;
+                const unsigned m = __match_any_sync(act, d);
+                if ((m & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&h2[d], (uint32_t)__popc(m));
+            }
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
             uint32_t c = c1, b = 0;
