@@ -235,7 +235,7 @@ def run_ours(args):
             gbs = roi_bytes / (roi[0] * 1e-3) / 1e9
             roi_roof = {"bound": "hbm", "kernel": "roi_align_nhwc_kernel (box head)", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                         "traffic": None, "peak_source": which}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:          # the CPU baseline is reported at N=1 only
             ips, dt, n = cpu_reference_images_per_sec(1, 0)
             cpu_base = {"value": ips, "unit": "images/sec", "cores": n, "kind": "port", "sample": "1 image 3x800x1216 (1/8 of one step), oracle/network.py"}
 

@@ -1,4 +1,6 @@
 // detectorch_b200 -- C-ABI entry points for the stand-alone operators (include/detectorch_b200.h).
+#include <stdlib.h>
+
 #include "../../include/detectorch_b200.h"
 #include "conv_host.cuh"
 #include "roi_align.cuh"
@@ -80,9 +82,11 @@ extern "C" int dt_roi_align_forward_nchw_fast(const float* features, int batch, 
                                               int sampling_ratio, float* out, void* workspace, dt_stream_t stream) {
     if (num_rois <= 0) return 1;
     // channel slab: the largest divisor of C (multiple of 4) whose [CS][ph*pw] fp32 tile fits ~50 KB of shared memory
+    static int tile_kb = 0;      // smaller tiles = more resident CTAs and more L1 left for the gathers (tunable: DT_ROI_TILE_KB)
+    if (!tile_kb) { const char* e = getenv("DT_ROI_TILE_KB"); tile_kb = e ? atoi(e) : 28;      // measured on B200: 28 KB (128 channels x 49 bins) beats 56 / 14 / 7 KB if (tile_kb < 4) tile_kb = 4; if (tile_kb > 100) tile_kb = 100; }
     int cs = 0;
     for (int d = channels; d >= 4; --d)
-        if (channels % d == 0 && (d & 3) == 0 && (size_t)d * pooled_height * pooled_width * 4 <= 56 * 1024 && ((size_t)d * pooled_height * pooled_width * 4) % 16 == 0) { cs = d; break; }
+        if (channels % d == 0 && (d & 3) == 0 && (size_t)d * pooled_height * pooled_width * 4 <= (size_t)tile_kb * 1024 && ((size_t)d * pooled_height * pooled_width * 4) % 16 == 0) { cs = d; break; }
     const size_t tile_bytes = (size_t)cs * pooled_height * pooled_width * 4;
     if (sampling_ratio != 2 || (channels & 3) || pooled_height > kMaxPooled || pooled_width > kMaxPooled || cs == 0) {
         // outside the fast path's envelope: the exact kernel handles every configuration
@@ -99,7 +103,8 @@ extern "C" int dt_roi_align_forward_nchw_fast(const float* features, int batch, 
         DT_CHECK_CUDA(cudaFuncSetAttribute(roi_align_fast_nchw_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;
     }
-    const int grid = (int)(num_rois < (int64_t)kNumSMs * 4 ? num_rois : (int64_t)kNumSMs * 4);
+    const int per_sm = (int)(200 * 1024 / (tile_bytes + 2048)) < 8 ? (int)(200 * 1024 / (tile_bytes + 2048)) : 8;
+    const int grid = (int)(num_rois < (int64_t)kNumSMs * per_sm ? num_rois : (int64_t)kNumSMs * per_sm);
     roi_align_fast_nchw_out_kernel<<<grid, 256, tile_bytes, st>>>(nhwc, rois, (long long)num_rois, roi_cols, channels, cs, height, width, pooled_height,
                                                                   pooled_width, spatial_scale, out);
     DT_CHECK_CUDA(cudaGetLastError());
