@@ -82,8 +82,10 @@ extern "C" int dt_roi_align_forward_nchw_fast(const float* features, int batch, 
                                               int sampling_ratio, float* out, void* workspace, dt_stream_t stream) {
     if (num_rois <= 0) return 1;
     // channel slab: the largest divisor of C (multiple of 4) whose [CS][ph*pw] fp32 tile fits ~50 KB of shared memory
-    static int tile_kb = 0;      // smaller tiles = more resident CTAs and more L1 left for the gathers (tunable: DT_ROI_TILE_KB)
-    if (!tile_kb) { const char* e = getenv("DT_ROI_TILE_KB"); tile_kb = e ? atoi(e) : 28;      // measured on B200: 28 KB (128 channels x 49 bins) beats 56 / 14 / 7 KB if (tile_kb < 4) tile_kb = 4; if (tile_kb > 100) tile_kb = 100; }
+    // smaller tiles = more resident CTAs and more L1 left for the gathers; measured on B200: 28 KB (128 channels x 49 bins)
+    // beats 56 / 14 / 7 KB (tunable: DT_ROI_TILE_KB)
+    static int tile_kb = 0;
+    if (!tile_kb) { const char* e = getenv("DT_ROI_TILE_KB"); tile_kb = e ? atoi(e) : 28; if (tile_kb < 4) tile_kb = 4; if (tile_kb > 100) tile_kb = 100; }
     int cs = 0;
     for (int d = channels; d >= 4; --d)
         if (channels % d == 0 && (d & 3) == 0 && (size_t)d * pooled_height * pooled_width * 4 <= (size_t)tile_kb * 1024 && ((size_t)d * pooled_height * pooled_width * 4) % 16 == 0) { cs = d; break; }
