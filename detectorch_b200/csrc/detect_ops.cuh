@@ -99,38 +99,6 @@ static __global__ void subsample2_nhwc_kernel(const float* __restrict__ x, int B
     }
 }
 
-// NHWC [M, Cs] (first C channels) -> NCHW [B, C, HW]   (public-layout views of internal maps)
-static __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int B, int HW, int Cs, int C, float* __restrict__ y) {
-    __shared__ float tile[32][33];
-    const int b = blockIdx.z;
-    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int p = p0 + r, c = c0 + threadIdx.x;
-        tile[r][threadIdx.x] = (p < HW && c < C) ? x[((size_t)b * HW + p) * Cs + c] : 0.f;
-    }
-    __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int c = c0 + r, p = p0 + threadIdx.x;
-        if (c < C && p < HW) y[((size_t)b * C + c) * HW + p] = tile[threadIdx.x][r];
-    }
-}
-
-// NCHW [B,C,HW] -> NHWC [B,HW,C]
-static __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int B, int HW, int C, float* __restrict__ y) {
-    __shared__ float tile[32][33];
-    const int b = blockIdx.z;
-    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int c = c0 + r, p = p0 + threadIdx.x;
-        tile[r][threadIdx.x] = (p < HW && c < C) ? x[((size_t)b * C + c) * HW + p] : 0.f;
-    }
-    __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int p = p0 + r, c = c0 + threadIdx.x;
-        if (c < C && p < HW) y[((size_t)b * HW + p) * C + c] = tile[threadIdx.x][r];
-    }
-}
-
 // global average pool of the res5 head: x [R, S, C] (S = 7*7 positions, NHWC) -> y [R, C]   (torchvision avgpool, detector.py:136,191)
 static __global__ void avgpool_nhwc_kernel(const float* __restrict__ x, int R, int S, int C, float* __restrict__ y) {
     const int C4 = C >> 2;
