@@ -38,11 +38,11 @@ def parity(h=320, w=416, arch="resnet50"):
     t0 = time.time()
     S = net.detect_and_mask_fpn(img, P, arch)
     print("oracle forward %.2fs; dets %d" % (time.time() - t0, len(S["scores_final"])), flush=True)
-    eng = E.Engine(arch=arch, batch=1, height=h, width=w, emit_full_masks=True, det_cap=128)
+    eng = E.Engine(arch=arch, batch=1, height=h, width=w, emit_full_masks=True, det_cap=128, exact_roialign=True)
     eng.load_state_dict(P)
     eng.run(img.to(dev), 1.0)
     torch.cuda.synchronize()
-    print("engine ran", flush=True)
+    print("engine ran (exact_roialign=True, precise_mask=True)", flush=True)
     for i in range(4):
         cmp("C%d" % (i + 2), nhwc_to_nchw(eng.buffer("C%d" % (i + 2))), S["C"][i])
     for i in range(4):
