@@ -14,15 +14,23 @@ SIGNATURES = {
     "dt_version": (ctypes.c_char_p, []),
     "launch_roi_align_forward_cuda": (c_int, [c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_int, c_int,
                                               c_void_p, c_void_p]),
+    "launch_roi_align_backward_cuda": (c_int, [c_int, c_void_p, c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                               c_int, c_void_p]),
     "dt_roi_align_forward_nchw": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
                                           c_void_p, c_void_p]),
-    "dt_roi_align_fast_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
+    "dt_roi_align_fast_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int64, c_int, c_int]),
     "dt_roi_align_forward_nchw_fast": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
                                                c_void_p, c_void_p, c_void_p]),
     "dt_roi_align_forward_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                           c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dt_nms_workspace_bytes": (c_int64, [c_int64]),
     "dt_nms": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dt_segm_workspace_bytes": (c_int64, [c_int, c_int]),
+    "dt_segm_strings_bytes": (c_int64, [c_int, c_int]),
+    "dt_segm_rle": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                            c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dt_segm_paste": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                              c_void_p, c_void_p]),
     "dt_tf32_residual": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "dt_conv2d_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -4,6 +4,7 @@
 #include "../../include/detectorch_b200.h"
 #include "conv_host.cuh"
 #include "roi_align.cuh"
+#include "segm.cuh"
 #include "sort_nms.cuh"
 
 using namespace dt;
@@ -34,6 +35,23 @@ extern "C" int launch_roi_align_forward_cuda(const int outputElements, const flo
     if (per_roi <= 0) return 1;
     return dt_roi_align_forward_nchw(bottom_data, bottom_rois, outputElements / per_roi, 5, channels, height, width, pooled_height,
                                      pooled_width, spatial_scale, sampling_ratio, top_data, stream);
+}
+
+// Replaces lib/cppcuda_cffi/src/cuda/roi_align_backward_cuda_kernel.h:7-21 (exact signature).  bottom_diff [B,C,H,W] is
+// accumulated into (the caller zeroes it, lib/model/roi_align.py:117); nthreads = R*C*ph*pw.
+extern "C" int launch_roi_align_backward_cuda(const int nthreads, const float* top_diff, const int num_rois, const float spatial_scale,
+                                              const int channels, const int height, const int width, const int pooled_height,
+                                              const int pooled_width, const int sampling_ratio, float* bottom_diff, const float* bottom_rois,
+                                              int roi_cols, dt_stream_t stream) {
+    (void)nthreads;
+    if (num_rois <= 0 || channels <= 0) return 1;
+    if (roi_cols != 4 && roi_cols != 5) { fprintf(stderr, "[detectorch_b200] roi_align backward: rois must have 4 or 5 columns\n"); return 0; }
+    const int grid = num_rois < kNumSMs * 8 ? num_rois : kNumSMs * 8;
+    roi_align_backward_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(top_diff, bottom_rois, (long long)num_rois, roi_cols, channels, height,
+                                                                          width, pooled_height, pooled_width, spatial_scale, sampling_ratio,
+                                                                          bottom_diff);
+    DT_CHECK_CUDA(cudaGetLastError());
+    return 1;
 }
 
 extern "C" int dt_roi_align_forward_nhwc(const float* const* feats, const int* heights, const int* widths, const float* scales,
@@ -73,8 +91,41 @@ __global__ void nchw_to_nhwc_tr_kernel(const float* __restrict__ x, int HW, int 
 }
 }  // namespace
 
-extern "C" int64_t dt_roi_align_fast_workspace_bytes(int batch, int channels, int height, int width) {
-    return (int64_t)batch * channels * height * width * 4;
+namespace {
+// shared-memory-resident map variant: geometry of the launch, or false if the map slab does not fit
+struct SmemMapPlan { int group, nwarps, num_chunks, num_items; size_t smem; };
+bool smem_map_plan(int batch, int channels, int height, int width, int64_t num_rois, int ph, int pw, SmemMapPlan* pl) {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("DT_ROI_SMEM_MAP"); mode = e ? atoi(e) : 1; }
+    if (!mode) return false;
+    if (!((ph == 7 && pw == 7) || (ph == 14 && pw == 14)) || channels % kSlabC) return false;
+    const size_t hw = (size_t)height * width;
+    if ((size_t)(height - 1) * width > 65535) return false;      // row offsets are packed as uint16
+    const size_t map_bytes = ((hw + 7) / 8 * 8) * kSlabC * 4;
+    static int nwarps = 0;
+    if (!nwarps) { const char* e = getenv("DT_ROI_SMEM_WARPS"); nwarps = e ? atoi(e) : 24; if (nwarps < 4) nwarps = 4; if (nwarps > 24) nwarps = 24; }
+    pl->nwarps = nwarps;
+    pl->group = 3584 / ((ph + pw) * 32);
+    pl->smem = map_bytes + (size_t)pl->nwarps * pl->group * (ph + pw) * 32;
+    if (pl->smem > 227 * 1024) return false;
+    const int slabs = batch * (channels / kSlabC);
+    int a = kNumSMs, b = slabs;
+    while (b) { const int t = a % b; a = b; b = t; }
+    int chunks = kNumSMs / a;                                        // slabs * chunks is a multiple of the SM count
+    const int64_t per_pass = (int64_t)pl->nwarps * pl->group;       // RoIs one CTA covers per sweep of its warps
+    const int64_t max_chunks = (num_rois + per_pass - 1) / per_pass;
+    if (chunks > max_chunks) chunks = (int)max_chunks;
+    pl->num_chunks = chunks < 1 ? 1 : chunks;
+    pl->num_items = slabs * pl->num_chunks;
+    return true;
+}
+}  // namespace
+
+extern "C" int64_t dt_roi_align_fast_workspace_bytes(int batch, int channels, int height, int width, int64_t num_rois, int pooled_height,
+                                                     int pooled_width) {
+    const int64_t nhwc = ((int64_t)batch * channels * height * width * 4 + 255) / 256 * 256;
+    const int64_t tables = num_rois * (pooled_height + pooled_width) * (int64_t)sizeof(AxisBinPacked);
+    return nhwc + tables;
 }
 
 extern "C" int dt_roi_align_forward_nchw_fast(const float* features, int batch, const float* rois, int64_t num_rois, int roi_cols, int channels,
@@ -98,6 +149,34 @@ extern "C" int dt_roi_align_forward_nchw_fast(const float* features, int batch, 
     cudaStream_t st = (cudaStream_t)stream;
     float* nhwc = reinterpret_cast<float*>(workspace);
     const int HW = height * width;
+    SmemMapPlan pl;
+    if (smem_map_plan(batch, channels, height, width, num_rois, pooled_height, pooled_width, &pl)) {
+        AxisBinPacked* tab = reinterpret_cast<AxisBinPacked*>(reinterpret_cast<uint8_t*>(workspace) +
+                                                              ((size_t)batch * channels * HW * 4 + 255) / 256 * 256);
+        const long long ents = (long long)num_rois * (pooled_height + pooled_width);
+        roi_tables_kernel<<<(unsigned)((ents + 255) / 256), 256, 0, st>>>(rois, (long long)num_rois, roi_cols, spatial_scale, height, width,
+                                                                         pooled_height, pooled_width, batch, tab);
+        DT_CHECK_CUDA(cudaGetLastError());
+        const int grid = pl.num_items < kNumSMs ? pl.num_items : kNumSMs;
+#define DT_LAUNCH_SMEM_MAP(PHW, BATCHED)                                                                                                   \
+    {                                                                                                                                      \
+        static bool attr = false;                                                                                                          \
+        if (!attr) {                                                                                                                       \
+            DT_CHECK_CUDA(cudaFuncSetAttribute(roi_align_smem_map_kernel<PHW, PHW, BATCHED>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                               227 * 1024));                                                                              \
+            attr = true;                                                                                                                   \
+        }                                                                                                                                  \
+        roi_align_smem_map_kernel<PHW, PHW, BATCHED><<<grid, pl.nwarps * 32, pl.smem, st>>>(features, tab, (long long)num_rois, channels,   \
+                                                                                           HW, pl.num_items, pl.num_chunks, pl.group, out); \
+    }
+        if (pooled_height == 7 && batch == 1) DT_LAUNCH_SMEM_MAP(7, false)
+        else if (pooled_height == 7) DT_LAUNCH_SMEM_MAP(7, true)
+        else if (batch == 1) DT_LAUNCH_SMEM_MAP(14, false)
+        else DT_LAUNCH_SMEM_MAP(14, true)
+#undef DT_LAUNCH_SMEM_MAP
+        DT_CHECK_CUDA(cudaGetLastError());
+        return 1;
+    }
     nchw_to_nhwc_tr_kernel<<<dim3((HW + 31) / 32, (channels + 31) / 32, batch), dim3(32, 8), 0, st>>>(features, HW, channels, nhwc);
     DT_CHECK_CUDA(cudaGetLastError());
     static bool attr_set = false;
@@ -359,5 +438,72 @@ extern "C" int dt_conv2d_nhwc(const float* x, int N, int H, int W, int Cin, int 
     ConvLayer L;
     if (!conv_build(s, &L)) return 0;
     DT_CHECK_CUDA(conv_launch(L, (cudaStream_t)stream));
+    return 1;
+}
+
+// ================================================================================== mask paste + COCO RLE (segm_results)
+namespace {
+constexpr int kSegmCharsPerRun = 4;     // staging bytes per run (maskApi's worst case is 7; typical masks need 1-2)
+size_t segm_smem_bytes(int M, int im_h, int im_w) {
+    const int S = M + 2;
+    return (size_t)((S * S + 3) & ~3) * 4 + (size_t)im_h * sizeof(SegmRowCoef) + (size_t)(im_w + 2) * 4 + 40 * 4;
+}
+}  // namespace
+
+extern "C" int64_t dt_segm_workspace_bytes(int max_dets, int runs_cap) {
+    return (int64_t)max_dets * runs_cap * 4 + (int64_t)max_dets * runs_cap * kSegmCharsPerRun + (int64_t)max_dets * 4 + 256;
+}
+
+extern "C" int64_t dt_segm_strings_bytes(int max_dets, int runs_cap) { return (int64_t)max_dets * runs_cap * kSegmCharsPerRun; }
+
+extern "C" int dt_segm_rle(const float* masks, const int* classes, int num_mask_classes, int mask_size, const float* ref_boxes,
+                           const int* expanded_boxes, const int* num_dets_dev, int max_dets, int im_h, int im_w, float thresh_binarize,
+                           uint32_t* counts, int* num_counts, int runs_cap, uint8_t* strings, int64_t* str_offsets, int* overflow,
+                           void* workspace, dt_stream_t stream) {
+    if (max_dets <= 0) return 1;
+    if (!masks || (!ref_boxes && !expanded_boxes) || !counts || !num_counts || !strings || !str_offsets || !overflow || !workspace) {
+        fprintf(stderr, "dt_segm_rle: null argument\n");
+        return 0;
+    }
+    if (mask_size < 1 || mask_size > 126 || im_h < 1 || im_w < 1 || (int64_t)im_h * im_w >= (1ll << 32) || runs_cap < 2) {
+        fprintf(stderr, "dt_segm_rle: unsupported size (mask %d, image %dx%d, runs_cap %d)\n", mask_size, im_h, im_w, runs_cap);
+        return 0;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    uint32_t* positions = reinterpret_cast<uint32_t*>(ws);
+    uint8_t* staging = ws + (size_t)max_dets * runs_cap * 4;
+    int* str_len = reinterpret_cast<int*>(staging + (((size_t)max_dets * runs_cap * kSegmCharsPerRun + 15) / 16 * 16));
+    const size_t smem = segm_smem_bytes(mask_size, im_h, im_w);
+    if (smem > 200 * 1024) { fprintf(stderr, "dt_segm_rle: image too large for the row/column tables (%zu B)\n", smem); return 0; }
+    static size_t smem_set = 48 * 1024;
+    if (smem > smem_set) {
+        DT_CHECK_CUDA(cudaFuncSetAttribute(segm_rle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        smem_set = 200 * 1024;
+    }
+    DT_CHECK_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), st));
+    segm_rle_kernel<<<max_dets, 256, smem, st>>>(masks, classes, classes ? num_mask_classes : 1, mask_size, ref_boxes, expanded_boxes,
+                                                 num_dets_dev, im_h, im_w, thresh_binarize, positions, counts, num_counts, runs_cap,
+                                                 staging, str_len, runs_cap * kSegmCharsPerRun, overflow);
+    DT_CHECK_CUDA(cudaGetLastError());
+    segm_compact_kernel<<<max_dets, 256, 0, st>>>(staging, str_len, max_dets, runs_cap * kSegmCharsPerRun, strings,
+                                                  reinterpret_cast<long long*>(str_offsets));
+    DT_CHECK_CUDA(cudaGetLastError());
+    return 1;
+}
+
+extern "C" int dt_segm_paste(const float* masks, const int* classes, int num_mask_classes, int mask_size, const float* ref_boxes,
+                             const int* expanded_boxes, const int* num_dets_dev, int max_dets, int im_h, int im_w, float thresh_binarize,
+                             uint8_t* out, dt_stream_t stream) {
+    if (max_dets <= 0) return 1;
+    if (!masks || (!ref_boxes && !expanded_boxes) || !out || mask_size < 1 || mask_size > 126) {
+        fprintf(stderr, "dt_segm_paste: bad argument\n");
+        return 0;
+    }
+    const int S = mask_size + 2;
+    segm_paste_kernel<<<max_dets, 256, (size_t)S * S * 4, (cudaStream_t)stream>>>(masks, classes, classes ? num_mask_classes : 1, mask_size,
+                                                                                  ref_boxes, expanded_boxes, num_dets_dev, im_h, im_w,
+                                                                                  thresh_binarize, out);
+    DT_CHECK_CUDA(cudaGetLastError());
     return 1;
 }

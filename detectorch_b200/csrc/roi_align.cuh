@@ -343,4 +343,157 @@ static __global__ void __launch_bounds__(256) roi_align_fast_nchw_out_kernel(con
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// ---------------------------------------------------------------------------------- shared-memory-resident map variant
+// When a slab of kSlabC channels of the whole [H,W] map fits in shared memory (H*W*48 B + tables <= 227 KB: any map up to
+// ~5000 cells, e.g. the 50x68 stride-16 map of the microbench), the gathers never leave the SM: a CTA loads one 8-channel
+// slab as two planes of float4 (channels 0-3 / 4-7) indexed by the pixel number with its low 3 bits XOR-ed with bits 3..5
+// (the 128-bit tap loads of a quarter-warp then fall in different bank groups for the common bin strides 1, 2, 4, 8), then
+// sweeps a chunk of RoIs.  The per-RoI AxisBin tables are computed once by roi_tables_kernel (they are shared by all
+// C/8 slabs), each warp copies the tables of a group of RoIs into its private shared-memory area (no block barriers), lanes
+// run over (RoI, bin) with the 8 channels in registers, and the stores of a warp cover 32 consecutive bins of one channel
+// plane (coalesced).  Arithmetic and summation order are those of roi_align_fast_nhwc_kernel => identical results.
+struct __align__(16) AxisBinPacked {
+    float w[4];
+    unsigned short idx[4];   // x taps: column; y taps: row * W (pixel index of the row start)
+    int n;
+    int batch;               // entry 0 of a RoI: batch index (-1: skip)
+};
+static constexpr int kSlabC = 8;
+__host__ __device__ __forceinline__ int slab_swizzle(int p) { return p ^ ((p >> 3) & 7); }
+
+static __global__ void __launch_bounds__(256) roi_tables_kernel(const float* __restrict__ rois, long long num_rois, int roi_cols, float scale, int H,
+                                                                int W, int PH, int PW, int batch, AxisBinPacked* __restrict__ tab) {
+    const int ents = PH + PW;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_rois * ents) return;
+    const long long n = t / ents;
+    const int e = (int)(t % ents);
+    const RoiGeom g = roi_geom(rois + n * roi_cols, roi_cols, scale, PH, PW, 2);
+    const AxisBin b = e < PH ? axis_bin2(g.start_h, e, g.bin_h, H) : axis_bin2(g.start_w, e - PH, g.bin_w, W);
+    AxisBinPacked o;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { o.w[j] = b.w[j]; o.idx[j] = (unsigned short)(e < PH ? b.idx[j] * W : b.idx[j]); }
+    o.n = b.n;
+    o.batch = (g.batch >= 0 && g.batch < batch) ? g.batch : -1;
+    tab[t] = o;
+}
+
+template <int PH, int PW, bool kBatched>
+static __global__ void __launch_bounds__(768, 1) roi_align_smem_map_kernel(const float* __restrict__ feat, const AxisBinPacked* __restrict__ tab,
+                                                                          long long num_rois, int C, int HW, int num_items, int num_chunks,
+                                                                          int group, float* __restrict__ out) {
+    extern __shared__ __align__(128) uint8_t roi_smem[];
+    constexpr int ENTS = PH + PW, BINS = PH * PW;
+    float* map = reinterpret_cast<float*>(roi_smem);                                              // [2][HW8] float4, swizzled
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int HW8 = (HW + 7) & ~7;
+    const float4* map4 = reinterpret_cast<const float4*>(map);
+    const size_t map_bytes = (size_t)HW8 * kSlabC * 4;
+    uint4* wtab = reinterpret_cast<uint4*>(roi_smem + map_bytes) + (size_t)warp * group * ENTS * 2;  // this warp's [group][ENTS] tables
+    const int slabs_per_image = C / kSlabC;
+    const long long chunk_len = (num_rois + num_chunks - 1) / num_chunks;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int chunk = item % num_chunks;
+        const int slab = item / num_chunks;               // (image, channel slab)
+        const int image = slab / slabs_per_image;
+        const int c0 = (slab % slabs_per_image) * kSlabC;
+        __syncthreads();                                  // everyone is done with the previous slab
+        const float* src = feat + ((size_t)image * C + c0) * HW;
+        for (int i = threadIdx.x; i < kSlabC * HW; i += blockDim.x) {
+            const int c = i / HW, p = i - c * HW;
+            map[((size_t)(c >> 2) * HW8 + slab_swizzle(p)) * 4 + (c & 3)] = __ldg(src + i);
+        }
+        __syncthreads();
+        const long long r_begin = chunk * chunk_len;
+        const long long r_end = r_begin + chunk_len < num_rois ? r_begin + chunk_len : num_rois;
+        for (long long g0 = r_begin + (long long)warp * group; g0 < r_end; g0 += (long long)nwarps * group) {
+            const int nr = (int)(r_end - g0 < group ? r_end - g0 : group);
+            __syncwarp();
+            // weights and (indices, n, batch) of an entry go to two separate arrays: consecutive entries are then consecutive
+            // 16-byte units (conflict-free for the 7 or 14 x-entries a quarter-warp reads)
+            const uint4* gsrc = reinterpret_cast<const uint4*>(tab + g0 * ENTS);
+            for (int i = lane; i < nr * ENTS * 2; i += 32) wtab[(i & 1) * group * ENTS + (i >> 1)] = __ldg(gsrc + i);
+            __syncwarp();
+            const uint4* wmeta = wtab + group * ENTS;
+            for (int t = lane; t < nr * BINS; t += 32) {
+                const int rl = t / BINS, bin = t - rl * BINS;
+                const int py = bin / PW, px = bin - py * PW;
+                const int iy = rl * ENTS + py, ix = rl * ENTS + PH + px;
+                const uint4 ymeta = wmeta[iy], xmeta = wmeta[ix];
+                if (kBatched && (int)wmeta[rl * ENTS].w != image) continue;
+                const float4 wy4 = *reinterpret_cast<const float4*>(wtab + iy);
+                const float4 wx4 = *reinterpret_cast<const float4*>(wtab + ix);
+                const float wy[4] = {wy4.x, wy4.y, wy4.z, wy4.w}, wx[4] = {wx4.x, wx4.y, wx4.z, wx4.w};
+                const int yi[4] = {(int)(ymeta.x & 0xffff), (int)(ymeta.x >> 16), (int)(ymeta.y & 0xffff), (int)(ymeta.y >> 16)};
+                const int xi[4] = {(int)(xmeta.x & 0xffff), (int)(xmeta.x >> 16), (int)(xmeta.y & 0xffff), (int)(xmeta.y >> 16)};
+                const int ny = (int)ymeta.z, nx = (int)xmeta.z;
+                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if (r < ny) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            if (c < nx) {
+                                const int sp = slab_swizzle(yi[r] + xi[c]);
+                                const float4 v0 = map4[sp], v1 = map4[HW8 + sp];
+                                const float w = wy[r] * wx[c];
+                                a0.x = fmaf(w, v0.x, a0.x); a0.y = fmaf(w, v0.y, a0.y); a0.z = fmaf(w, v0.z, a0.z); a0.w = fmaf(w, v0.w, a0.w);
+                                a1.x = fmaf(w, v1.x, a1.x); a1.y = fmaf(w, v1.y, a1.y); a1.z = fmaf(w, v1.z, a1.z); a1.w = fmaf(w, v1.w, a1.w);
+                            }
+                        }
+                    }
+                }
+                float* o = out + ((size_t)(g0 + rl) * C + c0) * BINS + bin;
+                o[0] = a0.x; o[BINS] = a0.y; o[2 * BINS] = a0.z; o[3 * BINS] = a0.w;
+                o[4 * BINS] = a1.x; o[5 * BINS] = a1.y; o[6 * BINS] = a1.z; o[7 * BINS] = a1.w;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- backward (training-side caller of b1-b4)
+// d(features) of RoIAlign: every pooled gradient element is scattered to the 4 cells of each of its samples with the bilinear
+// weights / sample count.  Same atomic scatter as the reference kernel (lib/cppcuda_cffi/src/cuda/roi_align_backward_cuda_kernel.cu
+// :100-207): fp32 atomics, so the summation order (and the last bits) vary from run to run exactly as they do there.  One CTA per
+// RoI; the 1-D sample tables are built once per RoI and shared by all channels; a warp reads a contiguous run of top_diff.
+static __global__ void __launch_bounds__(256) roi_align_backward_nchw_kernel(const float* __restrict__ top_diff, const float* __restrict__ rois,
+                                                                             long long num_rois, int roi_cols, int C, int H, int W, int PH, int PW,
+                                                                             float scale, int sampling_ratio, float* __restrict__ bottom_diff) {
+    __shared__ AxisTap ytab[kMaxAxisSamples];
+    __shared__ AxisTap xtab[kMaxAxisSamples];
+    for (long long n = blockIdx.x; n < num_rois; n += gridDim.x) {
+        const RoiGeom g = roi_geom(rois + n * roi_cols, roi_cols, scale, PH, PW, sampling_ratio);
+        const bool tabled = PH * g.grid_h <= kMaxAxisSamples && PW * g.grid_w <= kMaxAxisSamples;
+        __syncthreads();
+        if (tabled) {
+            for (int i = threadIdx.x; i < PH * g.grid_h; i += blockDim.x)
+                ytab[i] = axis_tap(sample_coord(g.start_h, i / g.grid_h, g.bin_h, i % g.grid_h, g.grid_h), H);
+            for (int i = threadIdx.x; i < PW * g.grid_w; i += blockDim.x)
+                xtab[i] = axis_tap(sample_coord(g.start_w, i / g.grid_w, g.bin_w, i % g.grid_w, g.grid_w), W);
+        }
+        __syncthreads();
+        const float count = (float)(g.grid_h * g.grid_w);
+        const float* td = top_diff + (size_t)n * C * PH * PW;
+        float* bd = bottom_diff + (size_t)g.batch * C * H * W;
+        const int per_roi = C * PH * PW;
+        for (int o = threadIdx.x; o < per_roi; o += blockDim.x) {
+            const int pw = o % PW, ph = (o / PW) % PH, c = o / (PW * PH);
+            const float gtop = td[o];
+            float* plane = bd + (size_t)c * H * W;
+            for (int iy = 0; iy < g.grid_h; ++iy) {
+                const AxisTap ty = tabled ? ytab[ph * g.grid_h + iy] : axis_tap(sample_coord(g.start_h, ph, g.bin_h, iy, g.grid_h), H);
+                for (int ix = 0; ix < g.grid_w; ++ix) {
+                    const AxisTap tx = tabled ? xtab[pw * g.grid_w + ix] : axis_tap(sample_coord(g.start_w, pw, g.bin_w, ix, g.grid_w), W);
+                    if (!(ty.valid && tx.valid)) continue;
+                    // g_k = top_diff * w_k / count, evaluated left to right as the reference does (:187-190)
+                    atomicAdd(plane + ty.lo * W + tx.lo, __fdiv_rn(__fmul_rn(gtop, __fmul_rn(ty.wl, tx.wl)), count));
+                    atomicAdd(plane + ty.lo * W + tx.hi, __fdiv_rn(__fmul_rn(gtop, __fmul_rn(ty.wl, tx.wh)), count));
+                    atomicAdd(plane + ty.hi * W + tx.lo, __fdiv_rn(__fmul_rn(gtop, __fmul_rn(ty.wh, tx.wl)), count));
+                    atomicAdd(plane + ty.hi * W + tx.hi, __fdiv_rn(__fmul_rn(gtop, __fmul_rn(ty.wh, tx.wh)), count));
+                }
+            }
+        }
+    }
+}
+
 }  // namespace dt

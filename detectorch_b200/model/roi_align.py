@@ -3,6 +3,7 @@ RoIAlign :150-169, preprocess_rois :172-188) over the sm_100a kernel.  Same name
 and error behaviour; CUDA only (the reference's CPU branch is the parity oracle, not a product path)."""
 import torch
 from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 from torch.nn.modules.module import Module
 
 from .. import ops
@@ -24,8 +25,14 @@ class RoIAlignFunction(Function):
                                           float(spatial_scale), int(sampling_ratio))
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_output):
-        raise NotImplementedError("RoIAlign backward (training) is outside the inference hot path of this build")
+        """Gradient w.r.t. the features (roi_align.py:91-147): zero-initialised [B,C,H,W], atomic scatter of the pooled gradient."""
+        if not grad_output.is_cuda:
+            raise TypeError('detectorch_b200 RoIAlign runs on CUDA tensors only (no CPU fallback)')
+        grad_input = ops.roi_align_backward_nchw(ctx.rois.contiguous(), grad_output.contiguous().float(), tuple(ctx.features_size),
+                                                 int(ctx.pooled_height), int(ctx.pooled_width), float(ctx.spatial_scale), int(ctx.sampling_ratio))
+        return grad_input, None, None, None, None, None
 
 
 class RoIAlign(Module):

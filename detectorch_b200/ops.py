@@ -42,6 +42,21 @@ def roi_align_forward_nchw(features, rois, pooled_height, pooled_width, spatial_
     return out
 
 
+def roi_align_backward_nchw(rois, grad_output, features_size, pooled_height, pooled_width, spatial_scale, sampling_ratio):
+    """grad_output [R,C,ph,pw], rois [R,4|5] -> gradient w.r.t. the NCHW features [B,C,H,W] (lib/model/roi_align.py:91-147)."""
+    _need_cuda(rois, grad_output)
+    B, C, H, W = [int(v) for v in features_size]
+    R = rois.size(0)
+    if grad_output.dim() != 4 or grad_output.size(0) != R or grad_output.size(1) != C:
+        raise RuntimeError("roi_align backward: grad_output must be [R,C,ph,pw]")
+    grad_input = torch.zeros((B, C, H, W), device=grad_output.device, dtype=torch.float32)
+    ok = _lib.lib().launch_roi_align_backward_cuda(int(grad_output.numel() & 0x7fffffff), _p(grad_output), R, float(spatial_scale), C, H, W,
+                                                   int(pooled_height), int(pooled_width), int(sampling_ratio), _p(grad_input), _p(rois),
+                                                   rois.size(1), _stream())
+    _lib.check(ok, "launch_roi_align_backward_cuda")
+    return grad_input
+
+
 def roi_align_forward_nchw_fast(features, rois, pooled_height, pooled_width, spatial_scale, sampling_ratio, out=None):
     """Same contract as roi_align_forward_nchw; sampling_ratio == 2 takes the separable / FMA fast path (fp32 re-association
     differences only), anything else is forwarded to the exact kernel."""
@@ -53,7 +68,7 @@ def roi_align_forward_nchw_fast(features, rois, pooled_height, pooled_width, spa
     if out is None:
         out = torch.empty((R, C, pooled_height, pooled_width), device=features.device, dtype=torch.float32)
     L = _lib.lib()
-    ws = torch.empty((L.dt_roi_align_fast_workspace_bytes(B, C, H, W),), dtype=torch.uint8, device=features.device)
+    ws = torch.empty((L.dt_roi_align_fast_workspace_bytes(B, C, H, W, R, int(pooled_height), int(pooled_width)),), dtype=torch.uint8, device=features.device)
     ok = L.dt_roi_align_forward_nchw_fast(_p(features), B, _p(rois), R, rois.size(1), C, H, W, int(pooled_height), int(pooled_width),
                                           float(spatial_scale), int(sampling_ratio), _p(out), _p(ws), _stream())
     _lib.check(ok, "dt_roi_align_forward_nchw_fast")
@@ -93,6 +108,66 @@ def nms(dets, thresh):
     cnt = torch.zeros((1,), dtype=torch.int32, device=dets.device)
     _lib.check(L.dt_nms(_p(dets), n, float(thresh), _p(keep), _p(cnt), _p(ws), _stream()), "dt_nms")
     return keep[:int(cnt.item())]
+
+
+def segm_rle(masks, classes, boxes, im_h, im_w, thresh=0.5, expanded=False, num_dets=None, runs_cap=4096):
+    """Mask paste + COCO RLE on the device (lib/utils/result_utils.py:170-228).
+    masks [D,K,M,M] (classes int32 [D] selects the plane) or [D,M,M]; boxes [D,4] fp32 reference boxes, or int32 already
+    expanded boxes when expanded=True.  Returns (counts list of uint32 arrays, strings list of bytes)."""
+    _need_cuda(masks, boxes, classes)
+    D = masks.size(0)
+    if D == 0:
+        return [], []
+    masks = masks.contiguous().float()
+    M = masks.size(-1)
+    K = masks.size(1) if masks.dim() == 4 else 1
+    boxes = boxes.contiguous()
+    if expanded and boxes.dtype != torch.int32:
+        raise TypeError("segm_rle: expanded boxes must be int32")
+    if not expanded:
+        boxes = boxes.float()
+    if classes is not None:
+        classes = classes.contiguous().to(torch.int32)
+    L = _lib.lib()
+    dev = masks.device
+    while True:
+        ws = torch.empty((L.dt_segm_workspace_bytes(D, runs_cap),), dtype=torch.uint8, device=dev)
+        counts = torch.empty((D, runs_cap), dtype=torch.int32, device=dev)
+        ncount = torch.empty((D,), dtype=torch.int32, device=dev)
+        strings = torch.empty((L.dt_segm_strings_bytes(D, runs_cap),), dtype=torch.uint8, device=dev)
+        offs = torch.empty((D + 1,), dtype=torch.int64, device=dev)
+        over = torch.zeros((1,), dtype=torch.int32, device=dev)
+        ok = L.dt_segm_rle(_p(masks), _p(classes), K, M, _p(None if expanded else boxes), _p(boxes if expanded else None), _p(num_dets), D,
+                           int(im_h), int(im_w), float(thresh), _p(counts), _p(ncount), runs_cap, _p(strings), _p(offs), _p(over), _p(ws),
+                           _stream())
+        _lib.check(ok, "dt_segm_rle")
+        need = int(over.item())
+        if need == 0:
+            break
+        runs_cap = max(2 * runs_cap, need + 1)     # a detection needed more runs than provisioned: grow and redo
+    offs_h = offs.cpu().numpy()
+    str_h = strings[:int(offs_h[-1])].cpu().numpy().tobytes()
+    n_h = ncount.cpu().numpy()
+    nmax = int(n_h.max()) if D else 0
+    cnt_h = counts[:, :max(nmax, 1)].cpu().numpy().view("uint32")
+    return [cnt_h[d, :n_h[d]].copy() for d in range(D)], [str_h[offs_h[d]:offs_h[d + 1]] for d in range(D)]
+
+
+def segm_paste(masks, classes, boxes, im_h, im_w, thresh=0.5, expanded=False, num_dets=None):
+    """Pasted binary masks uint8 [D, im_h, im_w] (the im_mask of result_utils.py:203-217 for every detection)."""
+    _need_cuda(masks, boxes, classes)
+    D = masks.size(0)
+    masks = masks.contiguous().float()
+    M = masks.size(-1)
+    K = masks.size(1) if masks.dim() == 4 else 1
+    boxes = boxes.contiguous() if expanded else boxes.contiguous().float()
+    if classes is not None:
+        classes = classes.contiguous().to(torch.int32)
+    out = torch.empty((D, int(im_h), int(im_w)), dtype=torch.uint8, device=masks.device)
+    ok = _lib.lib().dt_segm_paste(_p(masks), _p(classes), K, M, _p(None if expanded else boxes), _p(boxes if expanded else None),
+                                  _p(num_dets), D, int(im_h), int(im_w), float(thresh), _p(out), _stream())
+    _lib.check(ok, "dt_segm_paste")
+    return out
 
 
 def tf32_residual(w):

@@ -1,7 +1,7 @@
 """Mirror of the hot-path part of the reference lib/utils/result_utils.py: postprocess_output (:76-94)
 and box_results_with_nms_and_limit (:96-168), computed by the engine's on-device detection stage
 (decode with weights (10,10,5,5), clip, score > 0.05, per-class NMS 0.5, top-100) and returned in the
-reference's numpy structures."""
+reference's numpy structures; and of segm_results (:170-228): mask paste + COCO RLE on the device."""
 import numpy as np
 import torch
 
@@ -55,3 +55,46 @@ def postprocess_output(rois, scaling_factor, im_size, class_scores, bbox_deltas,
         m = classes == j
         cls_boxes[j] = np.hstack((boxes[m], scores[m][:, None])).astype(np.float32, copy=False)
     return scores, boxes, cls_boxes
+
+
+def segm_results(cls_boxes, masks, ref_boxes, im_h, im_w, num_classes=81, M=14, cls_specific_mask=True, thresh_binarize=0.5):
+    """Mirror of result_utils.segm_results (:170-228).  `masks` may be the CUDA tensor returned by model.mask_head
+    (no 25 MB device->host copy) or a numpy array [D, K, M, M]; returns cls_segms: per class a list of
+    {'size': [im_h, im_w], 'counts': str} exactly like pycocotools' encode() + .decode()."""
+    from .. import ops
+    n_per_class = [0] + [int(np.asarray(cls_boxes[j]).reshape(-1, 5).shape[0]) if len(cls_boxes[j]) else 0 for j in range(1, num_classes)]
+    D = int(sum(n_per_class))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    m = masks if torch.is_tensor(masks) else torch.from_numpy(np.ascontiguousarray(masks))
+    if m.shape[0] != D:
+        raise AssertionError("segm_results: %d masks for %d detections" % (m.shape[0], D))    # reference: assert mask_ind == masks.shape[0]
+    if m.shape[-1] != M:
+        raise ValueError("segm_results: masks are %dx%d but M=%d" % (m.shape[-1], m.shape[-1], M))
+    cls_segms = [[] for _ in range(num_classes)]
+    if D == 0:
+        return cls_segms
+    m = m.to(dev)
+    classes = np.repeat(np.arange(num_classes), n_per_class).astype(np.int32)
+    if not cls_specific_mask:
+        classes[:] = 0
+    # the reference expands the boxes on the host in the dtype it is given (boxes.py:245-261) and truncates to int32
+    rb = np.asarray(ref_boxes)
+    scale = (M + 2.0) / M
+    w_half = (rb[:, 2] - rb[:, 0]) * .5
+    h_half = (rb[:, 3] - rb[:, 1]) * .5
+    x_c = (rb[:, 2] + rb[:, 0]) * .5
+    y_c = (rb[:, 3] + rb[:, 1]) * .5
+    w_half *= scale
+    h_half *= scale
+    exp = np.zeros(rb.shape)
+    exp[:, 0] = x_c - w_half
+    exp[:, 2] = x_c + w_half
+    exp[:, 1] = y_c - h_half
+    exp[:, 3] = y_c + h_half
+    exp = torch.from_numpy(exp.astype(np.int32)).to(dev)
+    _, strings = ops.segm_rle(m, torch.from_numpy(classes).to(dev), exp, im_h, im_w, thresh_binarize, expanded=True)
+    k = 0
+    for j in range(1, num_classes):
+        cls_segms[j] = [{'size': [int(im_h), int(im_w)], 'counts': strings[k + i].decode()} for i in range(n_per_class[j])]
+        k += n_per_class[j]
+    return cls_segms

@@ -34,6 +34,16 @@ int launch_roi_align_forward_cuda(const int outputElements, const float* bottom_
                                   const int pooled_height, const int pooled_width, const int sampling_ratio, float* top_data,
                                   dt_stream_t stream);
 
+/* RoIAlign backward (gradient w.r.t. the features), the training-side caller of the same boundary.
+ * Replaces: lib/cppcuda_cffi/src/cuda/roi_align_backward_cuda_kernel.h:7-21 (exact signature kept; called by
+ * lib/cppcuda_cffi/src/roi_align_backward_cuda.c and lib/model/roi_align.py:91-147).  top_diff [R,C,ph,pw];
+ * bottom_diff [B,C,H,W] is ACCUMULATED into (the caller zeroes it, roi_align.py:117); atomic fp32 scatter like the reference,
+ * so the last bits depend on the summation order exactly as they do there. */
+int launch_roi_align_backward_cuda(const int nthreads, const float* top_diff, const int num_rois, const float spatial_scale,
+                                   const int channels, const int height, const int width, const int pooled_height,
+                                   const int pooled_width, const int sampling_ratio, float* bottom_diff, const float* bottom_rois,
+                                   int roi_cols, dt_stream_t stream);
+
 /* 64-bit-safe variant (R*C*ph*pw may exceed 2^31, e.g. 100k RoIs x 256 ch x 14 x 14); roi_cols is 4 or 5
  * like the reference CPU loop (lib/cppcuda_cffi/src/cpp/roi_align_cpu_loop.h:5-17). */
 int dt_roi_align_forward_nchw(const float* features, const float* rois, int64_t num_rois, int roi_cols, int channels, int height,
@@ -43,9 +53,11 @@ int dt_roi_align_forward_nchw(const float* features, const float* rois, int64_t 
 /* Fast variant for sampling_ratio == 2 (the FPN configurations and the RoIAlign microbench): separable bilinear weights with
  * merged duplicate taps, fused multiply-adds, output tile assembled in shared memory and written by one bulk async copy per
  * RoI.  Same contract as dt_roi_align_forward_nchw (any other configuration is forwarded to it); results agree with the
- * exact kernel to fp32 re-association (~1e-7 relative).  workspace: dt_roi_align_fast_workspace_bytes() (an NHWC copy of
- * the feature map). */
-int64_t dt_roi_align_fast_workspace_bytes(int batch, int channels, int height, int width);
+ * exact kernel to fp32 re-association (~1e-7 relative).  Maps small enough for an 8-channel slab of the whole map to live in
+ * shared memory (H*W <= ~3600 cells, 7x7 or 14x14 bins) take the shared-memory-resident variant: the gathers never leave
+ * the SM.  workspace: dt_roi_align_fast_workspace_bytes() (an NHWC copy of the feature map + the per-RoI tap tables). */
+int64_t dt_roi_align_fast_workspace_bytes(int batch, int channels, int height, int width, int64_t num_rois, int pooled_height,
+                                          int pooled_width);
 int dt_roi_align_forward_nchw_fast(const float* features, int batch, const float* rois, int64_t num_rois, int roi_cols, int channels, int height,
                                    int width, int pooled_height, int pooled_width, float spatial_scale, int sampling_ratio, float* out,
                                    void* workspace, dt_stream_t stream);
@@ -66,6 +78,30 @@ int dt_roi_align_forward_nhwc(const float* const* feats_host_array, const int* h
  */
 int64_t dt_nms_workspace_bytes(int64_t n);
 int dt_nms(const float* dets, int n, float thresh, int64_t* keep_out, int* num_keep_out, void* workspace, dt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Mask paste + COCO run-length encoding (the step right after the path).
+ * Replaces: lib/utils/result_utils.py:170-228 (segm_results): per detection zero-pad the MxM mask by one cell, expand the
+ * reference box by (M+2)/M (lib/utils/boxes.py:245-261), truncate to int32, cv2.resize(float32, INTER_LINEAR) to the box,
+ * threshold, paste into an im_h x im_w image, pycocotools rleEncode + rleToString -- without ever materialising the image.
+ *   masks          [max_dets, num_mask_classes, M, M] with classes[d] selecting the plane, or [max_dets, M, M] (classes NULL)
+ *   ref_boxes      [max_dets,4] fp32 image-space boxes (expanded on the device), or expanded_boxes [max_dets,4] int32
+ *                  (already expanded and truncated by the caller); one of the two must be non-NULL
+ *   num_dets_dev   optional device int: detections >= *num_dets_dev produce empty results
+ *   counts         [max_dets, runs_cap] uint32 run lengths (column-major, zeros run first), num_counts[max_dets]
+ *   strings        dt_segm_strings_bytes() bytes: the compressed RLE strings back to back; str_offsets[max_dets+1]
+ *   overflow       device int: 0, or the number of runs a detection needed when runs_cap (or its string staging) was too small
+ * dt_segm_paste writes the pasted binary masks themselves, uint8 [max_dets, im_h, im_w].
+ */
+int64_t dt_segm_workspace_bytes(int max_dets, int runs_cap);
+int64_t dt_segm_strings_bytes(int max_dets, int runs_cap);
+int dt_segm_rle(const float* masks, const int* classes, int num_mask_classes, int mask_size, const float* ref_boxes,
+                const int* expanded_boxes, const int* num_dets_dev, int max_dets, int im_h, int im_w, float thresh_binarize,
+                uint32_t* counts, int* num_counts, int runs_cap, uint8_t* strings, int64_t* str_offsets, int* overflow, void* workspace,
+                dt_stream_t stream);
+int dt_segm_paste(const float* masks, const int* classes, int num_mask_classes, int mask_size, const float* ref_boxes,
+                  const int* expanded_boxes, const int* num_dets_dev, int max_dets, int im_h, int im_w, float thresh_binarize,
+                  uint8_t* out, dt_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Convolution / GEMM on tcgen05 tensor cores (3xTF32, fp32-accurate), NHWC activations.

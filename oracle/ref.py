@@ -16,6 +16,9 @@ results are bit-identical to the reference run on CPU):
   bbox_transform / clip       lib/utils/boxes.py:150-208
   box_results_with_nms_and_limit / postprocess_output   lib/utils/result_utils.py:76-168
   roi_align_forward           lib/cppcuda_cffi/src/cpp/roi_align_cpu_loop.cpp:118-224 (oracle/roi_align_ref.c)
+  expand_boxes / segm_results lib/utils/boxes.py:245-261, lib/utils/result_utils.py:170-228  
+  resize_linear_f32           cv2.resize(float32, INTER_LINEAR) -- OpenCV's own (non-IPP) algorithm, modules/imgproc/src/resize.cpp
+  rle_encode / rle_to_string  pycocotools maskApi.c rleEncode / rleToString (third-party, not installed here)
 
 Parity pinned: tests/test_oracle.py checks every function here against (a) the
 reference's own modules imported from /root/reference when that tree is
@@ -304,3 +307,159 @@ def postprocess_output(rois, scaling_factor, im_size, class_scores, bbox_deltas,
     pred = clip_tiled_boxes(bbox_transform(boxes, deltas, bbox_reg_weights), im)
     sc = class_scores.numpy() if torch.is_tensor(class_scores) else class_scores
     return box_results_with_nms_and_limit(sc, pred)
+
+
+# ------------------------------------------------------------------------------------------------ mask paste + COCO RLE
+# The step right after the hot path: lib/utils/result_utils.py:170-228.  Two third-party pieces:
+#  * cv2.resize(float32 30x30 -> (w, h), INTER_LINEAR).  OpenCV 4.13 is importable in the build container; with IPP switched
+#    off (cv2.ipp.setUseIPP(False)) resize_linear_f32 below is BIT-IDENTICAL to it (tests/test_oracle.py, and the committed
+#    golden vectors were produced by cv2 itself).  IPP-enabled builds use Intel's kernel, which differs by <= 1.6e-6 in value
+#    and flips ~2e-7 of the thresholded pixels; OpenCV's own algorithm is the one restated.
+#  * pycocotools.mask.encode (maskApi.c rleEncode + rleToString): NOT installed here and not vendored by the reference, so
+#    the RLE string is "parity unpinned" against pycocotools; it is restated from the published algorithm and checked by a
+#    decode round trip and hand-computed strings.
+def resize_linear_f32(src, w, h):
+    """OpenCV resize, CV_32F, INTER_LINEAR, 1 channel: horizontal pass then vertical pass, float coefficients
+    (resize.cpp: resizeGeneric_ / HResizeLinear / VResizeLinear; coefficient set-up in cv::resize)."""
+    f32 = np.float32
+    src = np.ascontiguousarray(src, dtype=f32)
+    sh, sw = src.shape
+    if 2 * w == sw and 2 * h == sh:
+        # cv::resize turns INTER_LINEAR into the "area fast" kernel when both scale factors are exactly 2: 2x2 box average,
+        # 4-wide SIMD body (a+b)+(c+d), scalar tail ((a+b)+c)+d, times 0.25f (ResizeAreaFast_ / ResizeAreaFastVec_SIMD_32f)
+        a, b, c, d = src[0::2, 0::2], src[0::2, 1::2], src[1::2, 0::2], src[1::2, 1::2]
+        simd = (((a + b).astype(f32) + (c + d).astype(f32)).astype(f32) * f32(.25)).astype(f32)
+        tail = ((((a + b).astype(f32) + c).astype(f32) + d).astype(f32) * f32(.25)).astype(f32)
+        return np.where(np.arange(w)[None, :] < (w & ~3), simd, tail).astype(f32)
+
+    def axis(dst, n):
+        scale = 1.0 / (float(dst) / n)                                   # double, as in cv::resize
+        f = ((np.arange(dst, dtype=np.float64) + 0.5) * scale - 0.5).astype(f32)
+        s = np.floor(f).astype(np.int64)
+        return s, (f - s.astype(f32)).astype(f32)
+
+    sx, fx = axis(w, sw)
+    sy, fy = axis(h, sh)
+    lo = sx < 0                                                          # x: clamped cells get weight (1, 0)
+    fx = np.where(lo, f32(0), fx); sx = np.where(lo, 0, sx)
+    hi = sx >= sw - 1
+    fx = np.where(hi, f32(0), fx); sx = np.where(hi, sw - 1, sx)
+    a0, a1 = (f32(1) - fx).astype(f32), fx
+    sx1 = np.minimum(sx + 1, sw - 1)
+    hbuf = ((src[:, sx] * a0[None, :]).astype(f32) + (src[:, sx1] * a1[None, :]).astype(f32)).astype(f32)
+    r0, r1 = np.clip(sy, 0, sh - 1), np.clip(sy + 1, 0, sh - 1)          # y: row indices are clipped, weights kept
+    b0, b1 = (f32(1) - fy).astype(f32), fy
+    return ((hbuf[r0, :] * b0[:, None]).astype(f32) + (hbuf[r1, :] * b1[:, None]).astype(f32)).astype(f32)
+
+
+def expand_boxes(boxes, scale):
+    """lib/utils/boxes.py:245-261 (fp32 arithmetic on fp32 boxes, result widened to float64)."""
+    w_half = (boxes[:, 2] - boxes[:, 0]) * .5
+    h_half = (boxes[:, 3] - boxes[:, 1]) * .5
+    x_c = (boxes[:, 2] + boxes[:, 0]) * .5
+    y_c = (boxes[:, 3] + boxes[:, 1]) * .5
+    w_half *= scale
+    h_half *= scale
+    out = np.zeros(boxes.shape)
+    out[:, 0] = x_c - w_half
+    out[:, 2] = x_c + w_half
+    out[:, 1] = y_c - h_half
+    out[:, 3] = y_c + h_half
+    return out
+
+
+def rle_encode(mask):
+    """maskApi.c rleEncode: run lengths of the column-major flattening, starting with the zeros run."""
+    flat = np.asarray(mask, dtype=np.uint8).flatten(order='F')
+    if flat.size == 0:
+        return np.zeros((1,), np.uint32)
+    change = np.flatnonzero(flat[1:] != flat[:-1]) + 1
+    pos = np.concatenate([[0], change, [flat.size]])
+    counts = np.diff(pos)
+    if flat[0] != 0:
+        counts = np.concatenate([[0], counts])
+    return counts.astype(np.uint32)
+
+
+def rle_to_string(counts):
+    """maskApi.c rleToString: LEB128-like, 5 data bits + continuation bit per char, offset 48; counts[i>2] are
+    delta-coded against counts[i-2]."""
+    out = bytearray()
+    cn = [int(c) for c in counts]
+    for i, x in enumerate(cn):
+        if i > 2:
+            x -= cn[i - 2]
+        more = True
+        while more:
+            c = x & 0x1f
+            x >>= 5
+            more = (x != -1) if (c & 0x10) else (x != 0)
+            if more:
+                c |= 0x20
+            out.append(c + 48)
+    return bytes(out)
+
+
+def rle_from_string(s):
+    """maskApi.c rleFrString (inverse of rle_to_string), used for the round-trip check."""
+    s = s if isinstance(s, (bytes, bytearray)) else s.encode()
+    counts, p = [], 0
+    while p < len(s):
+        x, k, more = 0, 0, True
+        while more:
+            c = s[p] - 48
+            x |= (c & 0x1f) << (5 * k)
+            more = bool(c & 0x20)
+            p += 1
+            k += 1
+            if not more and (c & 0x10):
+                x |= -1 << (5 * k)
+        if len(counts) > 2:
+            x += counts[-2]
+        counts.append(x)
+    return np.asarray(counts, dtype=np.uint32)
+
+
+def rle_decode(counts, h, w):
+    flat = np.zeros((h * w,), np.uint8)
+    pos, v = 0, 0
+    for c in counts:
+        flat[pos:pos + int(c)] = v
+        pos += int(c)
+        v ^= 1
+    return flat.reshape((w, h)).T
+
+
+def paste_mask(mask_mm, ref_box_i32, im_h, im_w, thresh_binarize=0.5):
+    """One detection of result_utils.py:195-217: zero-pad by one cell, resize to the (expanded, int32) box, threshold,
+    paste into an im_h x im_w uint8 image."""
+    M = mask_mm.shape[0]
+    padded = np.zeros((M + 2, M + 2), np.float32)
+    padded[1:-1, 1:-1] = mask_mm
+    w = max(int(ref_box_i32[2]) - int(ref_box_i32[0]) + 1, 1)
+    h = max(int(ref_box_i32[3]) - int(ref_box_i32[1]) + 1, 1)
+    m = (resize_linear_f32(padded, w, h) > thresh_binarize).astype(np.uint8)
+    im = np.zeros((im_h, im_w), np.uint8)
+    x0, x1 = max(int(ref_box_i32[0]), 0), min(int(ref_box_i32[2]) + 1, im_w)
+    y0, y1 = max(int(ref_box_i32[1]), 0), min(int(ref_box_i32[3]) + 1, im_h)
+    if x1 > x0 and y1 > y0:
+        im[y0:y1, x0:x1] = m[y0 - int(ref_box_i32[1]):y1 - int(ref_box_i32[1]), x0 - int(ref_box_i32[0]):x1 - int(ref_box_i32[0])]
+    return im
+
+
+def segm_results(cls_boxes, masks, ref_boxes, im_h, im_w, num_classes=81, M=14, cls_specific_mask=True, thresh_binarize=0.5):
+    """lib/utils/result_utils.py:170-228 with cv2.resize -> resize_linear_f32 and mask_util.encode -> rle_encode/rle_to_string."""
+    cls_segms = [[] for _ in range(num_classes)]
+    mask_ind = 0
+    scale = (M + 2.0) / M
+    ref_boxes = expand_boxes(ref_boxes, scale).astype(np.int32)
+    for j in range(1, num_classes):
+        segms = []
+        for _ in range(cls_boxes[j].shape[0]):
+            m = masks[mask_ind, j if cls_specific_mask else 0, :, :]
+            im_mask = paste_mask(m, ref_boxes[mask_ind], im_h, im_w, thresh_binarize)
+            segms.append({'size': [im_h, im_w], 'counts': rle_to_string(rle_encode(im_mask)).decode()})
+            mask_ind += 1
+        cls_segms[j] = segms
+    assert mask_ind == masks.shape[0]
+    return cls_segms

@@ -117,10 +117,52 @@ def nms():
                           "cpu_reference_ms": cpu_ms, "kept_ids_equal_cpu": equal}), flush=True)
 
 
+def segm():
+    """100 detections of one 800x1216 image, 28x28 masks -> COCO RLE strings.  GPU: dt_segm_rle (device masks
+    in, strings out, D2H of the strings included); CPU: the reference algorithm (cv2.resize when importable, else the numpy
+    restatement) + the restated maskApi RLE, single thread as the reference runs it."""
+    rng = np.random.RandomState(7)
+    im_h, im_w, D, M = 800, 1216, 100, 28
+    b = synth_rois(D, seed=3, W=im_w, H=im_h)
+    yy, xx = np.mgrid[0:M, 0:M].astype(np.float32) / M
+    masks = np.stack([np.clip(1 / (1 + np.exp(((xx - rng.uniform(.3, .7)) ** 2 + (yy - rng.uniform(.3, .7)) ** 2 - rng.uniform(.05, .2)) * 40))
+                              + 0.1 * rng.randn(M, M), 0, 1) for _ in range(D)]).astype(np.float32)
+    tm, tb = torch.from_numpy(masks).to(dev), torch.from_numpy(b).to(dev)
+    ms = time_cuda(lambda: ops.segm_rle(tm, None, tb, im_h, im_w), warm=2, reps=5)
+    ms_paste = time_cuda(lambda: ops.segm_paste(tm, None, tb, im_h, im_w), warm=2, reps=5)
+    counts, strings = ops.segm_rle(tm, None, tb, im_h, im_w)
+    exp = ref.expand_boxes(b, (M + 2.0) / M).astype(np.int32)
+    try:
+        import cv2
+        cv2.ipp.setUseIPP(False)
+        cv2.setNumThreads(1)
+        resize, kind = (lambda m, w, h: cv2.resize(m, (w, h))), "cv2.resize (IPP off) + restated maskApi RLE"
+    except Exception:
+        resize, kind = ref.resize_linear_f32, "numpy restatement"
+    t0 = time.perf_counter()
+    same = True
+    for d in range(D):
+        padded = np.zeros((M + 2, M + 2), np.float32)
+        padded[1:-1, 1:-1] = masks[d]
+        w, h = max(exp[d, 2] - exp[d, 0] + 1, 1), max(exp[d, 3] - exp[d, 1] + 1, 1)
+        m = (resize(padded, int(w), int(h)) > 0.5).astype(np.uint8)
+        im = np.zeros((im_h, im_w), np.uint8)
+        x0, x1, y0, y1 = max(exp[d, 0], 0), min(exp[d, 2] + 1, im_w), max(exp[d, 1], 0), min(exp[d, 3] + 1, im_h)
+        im[y0:y1, x0:x1] = m[y0 - exp[d, 1]:y1 - exp[d, 1], x0 - exp[d, 0]:x1 - exp[d, 0]]
+        s = ref.rle_to_string(ref.rle_encode(im))
+        same = same and (s == strings[d])
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    print(json.dumps({"bench": "segm_rle", "dets": D, "image": [im_h, im_w], "mask": M, "gpu_ms_rle_incl_d2h": ms, "gpu_ms_paste_uint8": ms_paste,
+                      "cpu_ms": cpu_ms, "cpu_kind": kind, "strings_equal_cpu": bool(same),
+                      "string_bytes": int(sum(len(s) for s in strings)), "avoided_d2h_bytes": D * 81 * M * M * 4}), flush=True)
+
+
 if __name__ == "__main__":
     print(json.dumps({"device": torch.cuda.get_device_name(0)}), flush=True)
-    which = sys.argv[1:] or ["roialign", "nms"]
+    which = sys.argv[1:] or ["roialign", "nms", "segm"]
     if "roialign" in which:
         roialign()
     if "nms" in which:
         nms()
+    if "segm" in which:
+        segm()

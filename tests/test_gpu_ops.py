@@ -82,8 +82,17 @@ def test_roi_align_fast_path_matches_exact(dev, G):
     r = torch.from_numpy(r).to(dev)
     for p in (7, 14):
         exact = ops.roi_align_forward_nchw(f, r, p, p, 1 / 16., 2)
-        fast = ops.roi_align_forward_nchw_fast(f, r, p, p, 1 / 16., 2)
+        fast = ops.roi_align_forward_nchw_fast(f, r, p, p, 1 / 16., 2)          # 50x68 map: shared-memory-resident variant
         assert float((exact - fast).abs().max()) < 2e-5
+    # a map too large for the shared-memory-resident variant (100x136 cells) takes the gather variant; ragged RoI counts
+    fb = torch.from_numpy(rng.randn(2, 16, 100, 136).astype(np.float32)).to(dev)
+    for n in (1, 7, 129, 3000):
+        for (ff, sc) in ((f, 1 / 16.), (fb, 1 / 8.)):
+            exact = ops.roi_align_forward_nchw(ff, r[:n].contiguous(), 7, 7, sc, 2)
+            fast = ops.roi_align_forward_nchw_fast(ff, r[:n].contiguous(), 7, 7, sc, 2)
+            assert float((exact - fast).abs().max()) < 2e-5
+    r4 = r[:, 1:].contiguous()                                                   # 4-column RoIs (batch index 0 implied)
+    assert float((ops.roi_align_forward_nchw(f[:1], r4, 7, 7, 1 / 16., 2) - ops.roi_align_forward_nchw_fast(f[:1], r4, 7, 7, 1 / 16., 2)).abs().max()) < 2e-5
     assert torch.equal(ops.roi_align_forward_nchw_fast(f, r, 14, 14, 1 / 16., 0), ops.roi_align_forward_nchw(f, r, 14, 14, 1 / 16., 0))
     gf, gr = torch.from_numpy(G["roi_feat"]).to(dev), torch.from_numpy(G["roi_rois"]).to(dev)
     assert np.abs(ops.roi_align_forward_nchw_fast(gf[:, :4].contiguous(), gr, 7, 7, 1 / 16., 2).cpu().numpy() - G["roi_out_p7_sr2_s16"][:, :4]).max() < 1e-5
@@ -99,6 +108,33 @@ def test_roi_align_mirror_module_and_errors(dev):
     assert np.array_equal(out.cpu().numpy(), ref.roi_align_forward(f, r4, 7, 7, 1 / 16., 2))
     with pytest.raises(TypeError):
         RoIAlignFunction.apply(torch.from_numpy(f).to(dev), torch.from_numpy(r4), 7, 7, 1 / 16., 2)     # device mismatch, roi_align.py:43-44
+
+
+def test_roi_align_backward(dev):
+    """launch_roi_align_backward_cuda (the reference's exported symbol) through the mirror's autograd Function: agrees with the
+    gradient of torchvision's CPU roi_align (aligned=False, the same caffe2 algorithm; its forward is bit-identical to the
+    reference loop) within fp32 atomic-summation noise, for adaptive and fixed sampling ratios."""
+    tv = pytest.importorskip("torchvision")
+    from torchvision.ops import roi_align as tv_roi_align
+    from detectorch_b200.model.roi_align import RoIAlignFunction
+    rng = np.random.RandomState(9)
+    f = torch.from_numpy(rng.randn(2, 6, 25, 38).astype(np.float32))
+    r = torch.from_numpy(np.hstack([rng.randint(0, 2, (60, 1)).astype(np.float32), _boxes(rng, 60, 600, 400)]))
+    for (p, sr) in ((7, 2), (14, 0), (5, 3)):
+        go = torch.from_numpy(rng.randn(60, 6, p, p).astype(np.float32))
+        fc = f.clone().requires_grad_(True)
+        tv_roi_align(fc, r, (p, p), 1 / 16., sr, aligned=False).backward(go)
+        fg = f.clone().to(dev).requires_grad_(True)
+        out = RoIAlignFunction.apply(fg, r.to(dev), p, p, 1 / 16., sr)
+        out.backward(go.to(dev))
+        want = fc.grad.numpy()
+        assert np.abs(fg.grad.cpu().numpy() - want).max() <= 2e-5 * max(1.0, np.abs(want).max())
+    r4 = r[:, 1:].contiguous()                                  # 4-column RoIs
+    from detectorch_b200 import ops
+    g4 = ops.roi_align_backward_nchw(r4.to(dev), go.to(dev), (1, 6, 25, 38), 5, 5, 1 / 16., 3)
+    r5 = torch.cat([torch.zeros(60, 1), r4], 1)
+    g5 = ops.roi_align_backward_nchw(r5.to(dev), go.to(dev), (1, 6, 25, 38), 5, 5, 1 / 16., 3)
+    assert float((g4 - g5).abs().max()) <= 1e-4
 
 
 def test_roi_align_full_size_properties(dev):
@@ -216,3 +252,78 @@ def test_conv_epilogues(dev):
     assert _conv_case(dev, 1, 25, 38, 256, 16, 1, 0, 1, sig=3) < 1e-4
     # single-pass TF32 is NOT fp32-accurate: this is why the product path runs 3 passes
     assert 1e-4 < _conv_case(dev, 1, 1, 256, 1024, 128, 1, 0, 1, passes=1) < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------ mask paste + RLE (8f rank 1)
+def _segm_golden():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "segm_golden.npz"))
+
+
+def test_segm_golden(dev):
+    """dt_segm_paste / dt_segm_rle against the fixtures produced by the reference's own segm_results (real cv2.resize)."""
+    from detectorch_b200 import ops
+    from detectorch_b200.utils import result_utils as ru
+    S = _segm_golden()
+    for tag, M in (("m28", 28), ("m14", 14)):
+        masks, boxes, cls = S[tag + "_masks"], S[tag + "_boxes"], S[tag + "_cls"]
+        im_h, im_w = [int(v) for v in S[tag + "_size"]]
+        D, K = masks.shape[:2]
+        want_bits = np.unpackbits(S[tag + "_pasted_bits"], axis=1)[:, :im_h * im_w].reshape(D, im_h, im_w)
+        tm, tb, tc = torch.from_numpy(masks).to(dev), torch.from_numpy(boxes).to(dev), torch.from_numpy(cls).to(dev)
+        pasted = ops.segm_paste(tm, tc, tb, im_h, im_w).cpu().numpy()
+        assert np.array_equal(pasted, want_bits)
+        counts, strings = ops.segm_rle(tm, tc, tb, im_h, im_w)
+        assert [s.decode() for s in strings] == [str(x) for x in S[tag + "_rle"]]
+        for d in range(D):
+            assert np.array_equal(counts[d], ref_mod().rle_encode(want_bits[d]))
+        # the mirror of result_utils.segm_results returns the reference's structure (device masks, no host copy of them)
+        cls_boxes = [[] for _ in range(K)]
+        for j in range(1, K):
+            cls_boxes[j] = np.hstack([boxes[cls == j], np.ones((int((cls == j).sum()), 1), np.float32)])
+        got = ru.segm_results(cls_boxes, tm, boxes, im_h, im_w, num_classes=K, M=M)
+        want = ref_mod().segm_results(cls_boxes, masks, boxes, im_h, im_w, num_classes=K, M=M)
+        assert got == want
+        assert ru.segm_results(cls_boxes, masks, boxes, im_h, im_w, num_classes=K, M=M) == want      # numpy masks are accepted too
+
+
+def ref_mod():
+    from oracle import ref
+    return ref
+
+
+def test_segm_full_size_and_edges(dev):
+    """800x1216 image, 100 detections (BASELINE headline shape): bit-exact against the oracle on a sample, and for every
+    detection decode(counts) == pasted mask and sum(counts) == H*W; tiny runs_cap exercises the grow-and-redo path; no
+    detections; class-agnostic masks."""
+    from detectorch_b200 import ops
+    ref = ref_mod()
+    rng = np.random.RandomState(21)
+    im_h, im_w, D, M = 800, 1216, 100, 28
+    b = _boxes(rng, D, im_w, im_h)
+    b[:6] = [[0, 0, im_w - 1, im_h - 1], [0, 0, 3, 3], [im_w - 9, im_h - 9, im_w - 1, im_h - 1], [600, 0, 620, im_h - 1], [0, 400, im_w - 1, 410],
+             [100, 100, 113, 113]]
+    yy, xx = np.mgrid[0:M, 0:M].astype(np.float32) / M
+    masks = np.stack([np.clip(1 / (1 + np.exp(((xx - rng.uniform(.3, .7)) ** 2 + (yy - rng.uniform(.3, .7)) ** 2 - rng.uniform(.05, .2)) * 40))
+                              + 0.2 * rng.randn(M, M), 0, 1) for _ in range(D)]).astype(np.float32)
+    masks[0] = 1.0                                                      # the whole image set: runs touch every border
+    tm, tb = torch.from_numpy(masks).to(dev), torch.from_numpy(b).to(dev)
+    pasted = ops.segm_paste(tm, None, tb, im_h, im_w)
+    counts, strings = ops.segm_rle(tm, None, tb, im_h, im_w, runs_cap=64)          # forces at least one regrow
+    exp = ref.expand_boxes(b, (M + 2.0) / M).astype(np.int32)
+    for d in range(D):
+        assert int(counts[d].astype(np.int64).sum()) == im_h * im_w
+        if d < 12:
+            want = ref.paste_mask(masks[d], exp[d], im_h, im_w)
+            assert np.array_equal(pasted[d].cpu().numpy(), want)
+            assert np.array_equal(counts[d], ref.rle_encode(want))
+            assert strings[d] == ref.rle_to_string(ref.rle_encode(want))
+    # decode on the device side of the comparison: cumulative run ends -> parity bit per pixel, column-major
+    for d in (0, 1, 2, 3, 4, 5, 17, 99):
+        ends = torch.from_numpy(np.cumsum(counts[d].astype(np.int64))).to(dev)
+        pos = torch.arange(im_h * im_w, device=dev)
+        bit = (torch.searchsorted(ends, pos, right=True) & 1).to(torch.uint8).reshape(im_w, im_h).t()
+        assert torch.equal(bit, pasted[d])
+    assert ops.segm_rle(tm[:0], None, tb[:0], im_h, im_w) == ([], [])
+    nd = torch.tensor([3], dtype=torch.int32, device=dev)
+    c3, s3 = ops.segm_rle(tm[:8], None, tb[:8], im_h, im_w, num_dets=nd)
+    assert [len(c) for c in c3[3:]] == [0] * 5 and s3[:3] == strings[:3]
