@@ -31,7 +31,12 @@ SIGNATURES = {
                             c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dt_segm_paste": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                               c_void_p, c_void_p]),
+    "dt_prep_image": (c_int, [c_void_p, c_int, c_int, c_void_p, ctypes.c_double, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "dt_tf32_residual": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "dt_fp16_split": (c_int, [c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p]),
+    "dt_conv2d_nhwc_f16x3": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                     c_void_p, c_int, c_void_p]),
     "dt_conv2d_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_void_p, c_int, c_void_p]),

@@ -424,21 +424,60 @@ extern "C" int dt_tf32_residual(const float* w, float* w_lo, int64_t n, dt_strea
     return 1;
 }
 
-extern "C" int dt_conv2d_nhwc(const float* x, int N, int H, int W, int Cin, int x_pix_stride, const float* w, const float* w_lo, int Cout,
-                              int kh, int kw, int pad, int stride, const float* scale, const float* shift, const float* residual,
-                              int res_mode, const float* up_src, int up_h, int up_w, int relu, int sigmoid_ch, int passes,
-                              int force_block_n, float* y, int y_pix_stride, dt_stream_t stream) {
+namespace {
+__global__ void fp16_split_kernel(const float* __restrict__ w, float mult, __half* __restrict__ hi, __half* __restrict__ lo, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = w[i] * mult;          // mult is a power of two: exact
+        const __half h = __float2half_rn(v);
+        hi[i] = h;
+        lo[i] = __float2half_rn(v - __half2float(h));
+    }
+}
+
+int conv2d_nhwc_impl(int kind, const float* x, int N, int H, int W, int Cin, int x_pix_stride, const void* w, const void* w_lo, int Cout, int kh,
+                     int kw, int pad, int stride, const float* scale, const float* shift, const float* residual, int res_mode,
+                     const float* up_src, int up_h, int up_w, int relu, int sigmoid_ch, int passes, int force_block_n, int* range_flag,
+                     float* y, int y_pix_stride, dt_stream_t stream) {
     ConvSpec s;
     memset(&s, 0, sizeof(s));
     s.x = x; s.N = N; s.H = H; s.W = W; s.Cin = Cin; s.x_pix_stride = x_pix_stride;
-    s.w_hi = w; s.w_lo = w_lo; s.Cout = Cout; s.kh = kh; s.kw = kw; s.pad = pad; s.stride = stride;
+    s.w_hi = w; s.w_lo = w_lo; s.kind = kind; s.range_flag = range_flag;
+    s.Cout = Cout; s.kh = kh; s.kw = kw; s.pad = pad; s.stride = stride;
     s.scale = scale; s.shift = shift; s.y = y; s.y_pix_stride = y_pix_stride;
     s.residual = residual; s.res_pix_stride = Cout; s.up_src = up_src; s.up_h = up_h; s.up_w = up_w;
     s.res_mode = res_mode; s.relu = relu; s.sigmoid_ch = sigmoid_ch; s.passes = passes; s.force_block_n = force_block_n;
+    s.precise = force_block_n < 0;
+    if (force_block_n < 0) s.force_block_n = 128;        // -1: the precise 128-wide tile (3 rotating accumulators)
     ConvLayer L;
     if (!conv_build(s, &L)) return 0;
     DT_CHECK_CUDA(conv_launch(L, (cudaStream_t)stream));
     return 1;
+}
+}  // namespace
+
+extern "C" int dt_fp16_split(const float* w, int64_t n, float multiplier, void* w_hi16, void* w_lo16, dt_stream_t stream) {
+    if (n <= 0) return 1;
+    const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+    fp16_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, multiplier, reinterpret_cast<__half*>(w_hi16), reinterpret_cast<__half*>(w_lo16),
+                                                             (long long)n);
+    DT_CHECK_CUDA(cudaGetLastError());
+    return 1;
+}
+
+extern "C" int dt_conv2d_nhwc(const float* x, int N, int H, int W, int Cin, int x_pix_stride, const float* w, const float* w_lo, int Cout,
+                              int kh, int kw, int pad, int stride, const float* scale, const float* shift, const float* residual,
+                              int res_mode, const float* up_src, int up_h, int up_w, int relu, int sigmoid_ch, int passes,
+                              int force_block_n, float* y, int y_pix_stride, dt_stream_t stream) {
+    return conv2d_nhwc_impl(KIND_TF32X3, x, N, H, W, Cin, x_pix_stride, w, w_lo, Cout, kh, kw, pad, stride, scale, shift, residual, res_mode,
+                            up_src, up_h, up_w, relu, sigmoid_ch, passes, force_block_n, nullptr, y, y_pix_stride, stream);
+}
+
+extern "C" int dt_conv2d_nhwc_f16x3(const float* x, int N, int H, int W, int Cin, int x_pix_stride, const void* w_hi16, const void* w_lo16,
+                                    int Cout, int kh, int kw, int pad, int stride, const float* scale, const float* shift,
+                                    const float* residual, int res_mode, const float* up_src, int up_h, int up_w, int relu, int sigmoid_ch,
+                                    int passes, int force_block_n, int* range_flag, float* y, int y_pix_stride, dt_stream_t stream) {
+    return conv2d_nhwc_impl(KIND_F16X3, x, N, H, W, Cin, x_pix_stride, w_hi16, w_lo16, Cout, kh, kw, pad, stride, scale, shift, residual,
+                            res_mode, up_src, up_h, up_w, relu, sigmoid_ch, passes, force_block_n, range_flag, y, y_pix_stride, stream);
 }
 
 // ================================================================================== mask paste + COCO RLE (segm_results)
@@ -504,6 +543,24 @@ extern "C" int dt_segm_paste(const float* masks, const int* classes, int num_mas
     segm_paste_kernel<<<max_dets, 256, (size_t)S * S * 4, (cudaStream_t)stream>>>(masks, classes, classes ? num_mask_classes : 1, mask_size,
                                                                                   ref_boxes, expanded_boxes, num_dets_dev, im_h, im_w,
                                                                                   thresh_binarize, out);
+    DT_CHECK_CUDA(cudaGetLastError());
+    return 1;
+}
+
+// ================================================================================== image pre-processing (prep_im_for_blob + im_list_to_blob)
+extern "C" int dt_prep_image(const uint8_t* image_hwc, int height, int width, const double* pixel_means, double im_scale, int out_height,
+                             int out_width, float* blob_chw, int blob_height, int blob_width, dt_stream_t stream) {
+    if (!image_hwc || !pixel_means || !blob_chw || height < 1 || width < 1 || !(im_scale > 0.0) || out_height < 1 || out_width < 1 ||
+        blob_height < out_height || blob_width < out_width) {
+        fprintf(stderr, "dt_prep_image: bad argument\n");
+        return 0;
+    }
+    const double inv_scale = 1.0 / im_scale;
+    // cv::resize: INTER_LINEAR becomes the area-fast kernel when both scale factors are exactly 2
+    const int area2 = (fabs(inv_scale - 2.0) < 2.220446049250313e-16 && out_height * 2 <= height && out_width * 2 <= width) ? 1 : 0;
+    dim3 grid((blob_width + 255) / 256, blob_height);
+    prep_image_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(image_hwc, height, width, pixel_means[0], pixel_means[1], pixel_means[2], inv_scale,
+                                                             out_height, out_width, area2, blob_chw, blob_height, blob_width);
     DT_CHECK_CUDA(cudaGetLastError());
     return 1;
 }

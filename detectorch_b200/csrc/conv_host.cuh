@@ -68,12 +68,31 @@ inline bool make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_
     return true;
 }
 
+// 2D fp16 weight map {K (contiguous), rows}, box {32 elements = 64 bytes, rows}, SWIZZLE_64B (KIND_F16X3)
+inline bool make_tmap_2d_f16(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t s1, uint32_t b0, uint32_t b1) {
+    auto fn = get_tmap_encode();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {d0, d1};
+    cuuint64_t strides[1] = {s1};
+    cuuint32_t box[2] = {b0, b1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "[detectorch_b200] cuTensorMapEncodeTiled(2d f16) failed: %d dims=(%llu,%llu) stride=%llu box=(%u,%u)\n", (int)r,
+                (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)s1, b0, b1);
+        return false;
+    }
+    return true;
+}
+
 // A conv layer instance: everything needed to (re)launch it.  Built once per (layer, shape).
 struct ConvLayer {
     ConvParams p;
     int block_n;
     int nmain = 1;      // rotating main-term accumulators (3 = precise: shorter truncating accumulation chains)
     bool two_sm = true; // cta_group::2 MMA (default) vs 1-SM MMA + multicast (DT_CONV_1SM=1)
+    int kind = KIND_TF32X3;
     dim3 grid;
     bool valid = false;
 };
@@ -82,7 +101,9 @@ struct ConvLayer {
 struct ConvSpec {
     const float* x; int N, H, W, Cin;          // input  [N,H,W,Cin], Cin % 32 == 0
     int x_pix_stride;                          // floats between consecutive pixels of x (>= Cin; lets x be a channel slice)
-    const float* w_hi; const float* w_lo;      // [Cout_rows][kh*kw*Cin] K-major
+    const void* w_hi; const void* w_lo;        // [Cout_rows][kh*kw*Cin] K-major: fp32 (w, w - trunc_tf32(w)) or fp16 (hi, lo) for KIND_F16X3
+    int kind;                                  // ConvKind
+    int* range_flag;                           // KIND_F16X3: device flag raised when an activation does not fit fp16
     int Cout;                                  // output channels, multiple of 4
     int kh, kw, pad, stride;
     const float* scale; const float* shift;    // [Cout]
@@ -162,8 +183,15 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
                       s.stride, s.stride))
         return false;
     // each CTA of a pair fetches half of the BLOCK_N weight rows and multicasts them
-    if (!make_tmap_2d(&p.tm_bhi, s.w_hi, K, s.Cout, (uint64_t)K * 4, 32, bn / 2)) return false;
-    if (!make_tmap_2d(&p.tm_blo, s.w_lo ? s.w_lo : s.w_hi, K, s.Cout, (uint64_t)K * 4, 32, bn / 2)) return false;
+    if (s.kind == KIND_F16X3) {
+        if (!make_tmap_2d_f16(&p.tm_bhi, s.w_hi, K, s.Cout, (uint64_t)K * 2, 32, bn / 2)) return false;
+        if (!make_tmap_2d_f16(&p.tm_blo, s.w_lo ? s.w_lo : s.w_hi, K, s.Cout, (uint64_t)K * 2, 32, bn / 2)) return false;
+    } else {
+        if (!make_tmap_2d(&p.tm_bhi, s.w_hi, K, s.Cout, (uint64_t)K * 4, 32, bn / 2)) return false;
+        if (!make_tmap_2d(&p.tm_blo, s.w_lo ? s.w_lo : s.w_hi, K, s.Cout, (uint64_t)K * 4, 32, bn / 2)) return false;
+    }
+    L->kind = s.kind == KIND_F16X3 ? KIND_F16X3 : KIND_TF32X3;
+    p.range_flag = s.range_flag;
     const uint64_t ys = (uint64_t)s.y_pix_stride * 4;
     if (s.out_step == 0) {
         if (!make_tmap_4d(&p.tm_d, s.y, s.Cout, Wo, Ho, s.N, ys, ys * Wo, ys * Wo * Ho, 32, wbox, hbox, nbox)) return false;
@@ -226,31 +254,33 @@ inline bool conv_build_stem(const float* x4, int B, int Hp, int Wp, int H1, int 
     return true;
 }
 
-template <int BN, int NM, bool TWO>
+template <int BN, int NM, bool TWO, int KIND>
 inline cudaError_t conv_launch_cfg(const ConvLayer& L, cudaStream_t stream) {
+    using Cfg = ConvCfg<BN, NM, TWO, KIND>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel<BN, NM, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN, NM, TWO>::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel<BN, NM, TWO, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    conv_tcgen05_kernel<BN, NM, TWO><<<L.grid, ConvCfg<BN, NM, TWO>::THREADS, ConvCfg<BN, NM, TWO>::SMEM_BYTES, stream>>>(L.p);
+    conv_tcgen05_kernel<BN, NM, TWO, KIND><<<L.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(L.p);
     return cudaGetLastError();
 }
 
-template <bool TWO>
+template <bool TWO, int KIND>
 inline cudaError_t conv_launch_sm(const ConvLayer& L, cudaStream_t stream) {
     switch (L.block_n) {
-        case 64: return conv_launch_cfg<64, 3, TWO>(L, stream);
-        case 128: return L.nmain == 3 ? conv_launch_cfg<128, 3, TWO>(L, stream) : conv_launch_cfg<128, 1, TWO>(L, stream);
-        case 256: return conv_launch_cfg<256, 1, TWO>(L, stream);
+        case 64: return conv_launch_cfg<64, 3, TWO, KIND>(L, stream);
+        case 128: return L.nmain == 3 ? conv_launch_cfg<128, 3, TWO, KIND>(L, stream) : conv_launch_cfg<128, 1, TWO, KIND>(L, stream);
+        case 256: return conv_launch_cfg<256, 1, TWO, KIND>(L, stream);
         default: return cudaErrorInvalidValue;
     }
 }
 
 inline cudaError_t conv_launch(const ConvLayer& L, cudaStream_t stream) {
     if (!L.valid) return cudaErrorInvalidValue;
-    return L.two_sm ? conv_launch_sm<true>(L, stream) : conv_launch_sm<false>(L, stream);
+    if (L.kind == KIND_F16X3) return L.two_sm ? conv_launch_sm<true, KIND_F16X3>(L, stream) : conv_launch_sm<false, KIND_F16X3>(L, stream);
+    return L.two_sm ? conv_launch_sm<true, KIND_TF32X3>(L, stream) : conv_launch_sm<false, KIND_TF32X3>(L, stream);
 }
 
 }  // namespace dt

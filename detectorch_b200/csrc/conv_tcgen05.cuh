@@ -16,6 +16,13 @@
 // previous stage's MMAs run, and B_lo precomputed once per weight tensor.  `passes`==1 runs the
 // plain single-pass TF32 product (debug / speed-of-light reference).
 //
+// KIND_F16X3 (the engine default for every layer but the stem) runs the same three-term product on the kind::f16 pipe, which
+// issues at twice the tf32 rate: A = A_h + A_l with A_h = fp16(A), A_l = fp16(A - A_h) (22 mantissa bits, the same as the two
+// tf32 pieces), B_h / B_l likewise (precomputed, pre-scaled by a power of two so that B_l stays a normal fp16 number; the
+// epilogue scale undoes it exactly).  The fp32 A tile still arrives by TMA; the converter warps write A_h / A_l as two
+// 64-byte-row (SWIZZLE_64B) fp16 tiles.  fp16 has a 5-bit exponent: |A| >= 65504 raises a device flag (the engine then
+// reports it; the tf32 kind has no such limit).
+//
 // Tile: BLOCK_M = 128 output pixels (a wbox x hbox x nbox box of the NHWC output, so the same
 // TMA box geometry loads A for any filter tap and stores D, with hardware zero-fill doing the
 // padding and hardware clipping doing the edge masking), BLOCK_N = 64/128/256 output channels,
@@ -33,11 +40,14 @@
 // TMEM holds NMAIN rotating main-term accumulators + 1 cross-term accumulator per tile, double-buffered
 // when two tiles fit in the 512 columns.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace dt {
 
 enum ConvResidualMode { RES_NONE = 0, RES_TILE = 1, RES_UPSAMPLE2X = 2 };
+enum ConvKind { KIND_TF32X3 = 0, KIND_F16X3 = 1 };
 
 struct ConvParams {
     CUtensorMap tm_a;      // 4D {C, W, H, N} over the NHWC input (elementStrides carry the conv stride)
@@ -61,19 +71,22 @@ struct ConvParams {
     int relu;
     int sigmoid_ch;        // channels [0, sigmoid_ch) get a sigmoid (RPN objectness), after bias
     int res_mode;
-    int passes;            // 3 = 3xTF32 (default), 1 = single TF32
+    int passes;            // 3 = error-compensated three-term product (default), 1 = single pass
+    int* range_flag;       // KIND_F16X3: set to 1 when an activation does not fit fp16 (|x| >= 65504 or NaN); may be null
 };
 
-template <int BLOCK_N, int NMAIN, bool kTwoSM>
+template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND>
 struct ConvCfg {
     static constexpr int BLOCK_M = 128;
     static constexpr int BLOCK_K = 32;
-    static constexpr int A_BYTES = BLOCK_M * 128;                    // 16 KB
+    static constexpr int A_BYTES = BLOCK_M * 128;                    // 16 KB: the fp32 A tile as TMA delivers it
     // 1-SM MMA: every CTA holds the whole BLOCK_N-row weight tile (its half arrives by multicast from the peer).
     // 2-SM MMA (cta_group::2): every CTA holds only ITS half -> smaller stages, deeper pipeline, half the operand ingest per SM.
-    static constexpr int B_BYTES = (kTwoSM ? BLOCK_N / 2 : BLOCK_N) * 128;
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;    // A, A_lo, B_hi, B_lo
-    static constexpr int STAGES = kTwoSM ? (BLOCK_N == 256 ? 3 : 4) : ((BLOCK_N == 256) ? 2 : (BLOCK_N == 128 ? 3 : 4));
+    static constexpr int B_ROW_BYTES = KIND == KIND_F16X3 ? 64 : 128; // 32 k-elements per row
+    static constexpr int B_BYTES = (kTwoSM ? BLOCK_N / 2 : BLOCK_N) * B_ROW_BYTES;
+    // tf32: A, A_lo, B_hi, B_lo.   f16: A (fp32 staging), A_h + A_l (8 KB each, in the second 16 KB), B_h, B_l
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = (196608 / STAGE_BYTES) > 4 ? 4 : (196608 / STAGE_BYTES);
     static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
     static constexpr int EPI_BYTES = 2 * A_BYTES;                    // 2 x (128 rows x 32 channels) staging ring
     static constexpr int TILE_COLS = (NMAIN + 1) * BLOCK_N;          // TMEM columns of one tile's accumulators
@@ -87,9 +100,9 @@ struct ConvCfg {
     static_assert(8 * (NUM_BARS + 1) <= 256, "barrier area");
 };
 
-template <int BLOCK_N, int NMAIN, bool kTwoSM>
+template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
-    using Cfg = ConvCfg<BLOCK_N, NMAIN, kTwoSM>;
+    using Cfg = ConvCfg<BLOCK_N, NMAIN, kTwoSM, KIND>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int NBUF = Cfg::NBUF;
     extern __shared__ uint8_t smem_raw[];
@@ -190,7 +203,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
         }
     } else if (warp == 1) {
         // ================================================================ MMA issuer (one elected lane; 2-SM: leader CTA only)
-        constexpr uint32_t idesc = umma_idesc(2, kTwoSM ? 256 : 128, BLOCK_N);
+        constexpr uint32_t idesc = umma_idesc(KIND == KIND_F16X3 ? 0 : 2, kTwoSM ? 256 : 128, BLOCK_N);
+        // one K step of the instruction = 32 bytes of a row: 8 tf32 or 16 fp16 elements -> 4 or 2 steps per 32-element k-block
+        constexpr int KSTEPS = KIND == KIND_F16X3 ? 2 : 4;
+        auto mma = [&](uint32_t acc, uint64_t da_, uint64_t db_, uint32_t flag) {
+            if constexpr (KIND == KIND_F16X3) {
+                if constexpr (kTwoSM) umma_f16_2sm(acc, da_, db_, idesc, flag); else umma_f16(acc, da_, db_, idesc, flag);
+            } else {
+                if constexpr (kTwoSM) umma_tf32_2sm(acc, da_, db_, idesc, flag); else umma_tf32(acc, da_, db_, idesc, flag);
+            }
+        };
         uint32_t it = 0;
         int t = 0;
         for (int item = pair; item < num_items && (!kTwoSM || cta_rank == 0); item += num_pairs, ++t) {
@@ -202,17 +224,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
-                if constexpr (kTwoSM) mbar_wait_cluster(bar_conv(s), ph);   // both CTAs' TMA data landed and both A_lo tiles are published
-                else mbar_wait(bar_conv(s), ph);      // converters waited on full[s] and published A_lo
+                if constexpr (kTwoSM) mbar_wait_cluster(bar_conv(s), ph);   // both CTAs' TMA data landed and both converted A tiles are published
+                else mbar_wait(bar_conv(s), ph);      // converters waited on full[s] and published their tiles
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
-                    const uint64_t da = umma_desc_k_sw128(st);
-                    const uint64_t dal = umma_desc_k_sw128(st + Cfg::A_BYTES);
-                    const uint64_t dbh = umma_desc_k_sw128(st + 2 * Cfg::A_BYTES);
-                    const uint64_t dbl = umma_desc_k_sw128(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+                    uint64_t da, dal, dbh, dbl;      // "hi" A, "lo" A, "hi" B, "lo" B
+                    if constexpr (KIND == KIND_F16X3) {
+                        da = umma_desc_k_sw64(st + Cfg::A_BYTES);
+                        dal = umma_desc_k_sw64(st + Cfg::A_BYTES + Cfg::A_BYTES / 2);
+                        dbh = umma_desc_k_sw64(st + 2 * Cfg::A_BYTES);
+                        dbl = umma_desc_k_sw64(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+                    } else {
+                        da = umma_desc_k_sw128(st);
+                        dal = umma_desc_k_sw128(st + Cfg::A_BYTES);
+                        dbh = umma_desc_k_sw128(st + 2 * Cfg::A_BYTES);
+                        dbl = umma_desc_k_sw128(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+                    }
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {       // 4 x (K = 8 tf32 = 32 bytes) per 128-byte swizzle row
+                    for (int k = 0; k < KSTEPS; ++k) {
                         const uint64_t koff = (uint64_t)(k * 32 >> 4);
                         // The tensor core accumulates in fp32 with truncation, so every accumulate step costs up to 1 ulp of
                         // the running sum (a systematic shrink of ~0.18 * steps * 2^-23).  Two measures keep the chains short:
@@ -220,21 +250,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
                         //  * the main term rotates over NMAIN accumulators by k-block (summed with RN adds in the epilogue).
                         const uint32_t acc_main = acc0 + (uint32_t)((kb % NMAIN) * BLOCK_N);
                         const uint32_t main_flag = (kb >= NMAIN || k != 0) ? 1u : 0u;
-                        if constexpr (kTwoSM) {
-                            if (p.passes == 3) {
-                                const uint32_t acc_x = acc0 + (uint32_t)(NMAIN * BLOCK_N);
-                                umma_tf32_2sm(acc_x, dal + koff, dbh + koff, idesc, (kb | k) != 0);
-                                umma_tf32_2sm(acc_x, da + koff, dbl + koff, idesc, 1u);
-                            }
-                            umma_tf32_2sm(acc_main, da + koff, dbh + koff, idesc, main_flag);
-                        } else {
-                            if (p.passes == 3) {
-                                const uint32_t acc_x = acc0 + (uint32_t)(NMAIN * BLOCK_N);
-                                umma_tf32(acc_x, dal + koff, dbh + koff, idesc, (kb | k) != 0);
-                                umma_tf32(acc_x, da + koff, dbl + koff, idesc, 1u);
-                            }
-                            umma_tf32(acc_main, da + koff, dbh + koff, idesc, main_flag);
+                        if (p.passes == 3) {
+                            const uint32_t acc_x = acc0 + (uint32_t)(NMAIN * BLOCK_N);
+                            mma(acc_x, dal + koff, dbh + koff, (kb | k) != 0);
+                            mma(acc_x, da + koff, dbl + koff, 1u);
                         }
+                        mma(acc_main, da + koff, dbh + koff, main_flag);
                     }
                     if constexpr (kTwoSM) {
                         umma_commit_2sm_mcast(bar_empty(s), (uint16_t)3);                        // frees this stage in both CTAs
@@ -256,7 +277,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
                 mbar_wait(bar_full(s), ph);
-                if (p.passes == 3) {
+                if constexpr (KIND == KIND_F16X3) {
+                    // A_h = fp16(A), A_l = fp16(A - A_h): thread -> (row, 8-channel group); two 16-byte pieces of the 128B-swizzled
+                    // fp32 row in, one 16-byte piece of each 64B-swizzled fp16 row out (both access patterns are conflict-free)
+                    const uint8_t* a32 = smem_gen + s * Cfg::STAGE_BYTES;
+                    uint8_t* ah = smem_gen + s * Cfg::STAGE_BYTES + Cfg::A_BYTES;
+                    uint8_t* al = ah + Cfg::A_BYTES / 2;
+                    bool bad = false;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = ct, c8 = i;
+                        const float4 v0 = *reinterpret_cast<const float4*>(a32 + r * 128 + (((2 * c8) ^ (r & 7)) << 4));
+                        const float4 v1 = *reinterpret_cast<const float4*>(a32 + r * 128 + (((2 * c8 + 1) ^ (r & 7)) << 4));
+                        const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                        __half2 hh[4], ll[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const __half h0 = __float2half_rn(f[2 * j]), h1 = __float2half_rn(f[2 * j + 1]);
+                            bad = bad || !(fabsf(f[2 * j]) < 65504.f) || !(fabsf(f[2 * j + 1]) < 65504.f);
+                            hh[j] = __halves2half2(h0, h1);
+                            ll[j] = __halves2half2(__float2half_rn(f[2 * j] - __half2float(h0)), __float2half_rn(f[2 * j + 1] - __half2float(h1)));
+                        }
+                        const int off = r * 64 + ((c8 ^ ((r >> 1) & 3)) << 4);
+                        *reinterpret_cast<uint4*>(ah + off) = *reinterpret_cast<const uint4*>(hh);
+                        if (p.passes == 3) *reinterpret_cast<uint4*>(al + off) = *reinterpret_cast<const uint4*>(ll);
+                    }
+                    if (bad && p.range_flag) *p.range_flag = 1;
+                    fence_proxy_async_smem();
+                } else if (p.passes == 3) {
                     // A_lo = A - trunc_tf32(A), element-wise, so the swizzled placement is preserved verbatim
                     const float4* a = reinterpret_cast<const float4*>(smem_gen + s * Cfg::STAGE_BYTES);
                     float4* alo = reinterpret_cast<float4*>(smem_gen + s * Cfg::STAGE_BYTES + Cfg::A_BYTES);

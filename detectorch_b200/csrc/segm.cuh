@@ -329,4 +329,40 @@ static __global__ void __launch_bounds__(256) segm_paste_kernel(const float* __r
     }
 }
 
+// ---------------------------------------------------------------------------------- image pre-processing
+// lib/utils/blob.py:57-87 prep_im_for_blob (uint8 BGR HWC -> float32, minus the per-channel mean, cv2.resize(fx = fy = im_scale,
+// INTER_LINEAR)) fused with blob.py:27-55 im_list_to_blob (zero-pad to blob_h x blob_w, HWC -> CHW).  The resize is OpenCV's own
+// float kernel: coefficients from scale = 1 / im_scale (the fx/fy form of cv::resize), horizontal then vertical pass with separately
+// rounded products; im_scale == 0.5 takes OpenCV's area-fast path (2x2 box, ((a+b)+c)+d times 0.25f for 3 channels).
+static __global__ void __launch_bounds__(256) prep_image_kernel(const uint8_t* __restrict__ im, int h, int w, double m0, double m1, double m2,
+                                                                double inv_scale, int out_h, int out_w, int area2,
+                                                                float* __restrict__ blob, int blob_h, int blob_w) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= blob_w) return;
+    const size_t plane = (size_t)blob_h * blob_w;
+    float* o = blob + (size_t)y * blob_w + x;
+    if (y >= out_h || x >= out_w) { o[0] = 0.f; o[plane] = 0.f; o[2 * plane] = 0.f; return; }
+    const double mean[3] = {m0, m1, m2};
+    auto px = [&](int r, int cidx, int c) -> float { return (float)((double)im[((size_t)r * w + cidx) * 3 + c] - mean[c]); };
+    if (area2) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float a = px(2 * y, 2 * x, c), b = px(2 * y, 2 * x + 1, c), cc = px(2 * y + 1, 2 * x, c), d = px(2 * y + 1, 2 * x + 1, c);
+            o[c * plane] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(a, b), cc), d), 0.25f);
+        }
+        return;
+    }
+    const AxisCoef cx = resize_coef_x(x, inv_scale, w);
+    const AxisCoef cy = resize_coef(y, inv_scale);
+    const int r0 = min(max(cy.s, 0), h - 1), r1 = min(max(cy.s + 1, 0), h - 1);
+    const int x1 = min(cx.s + 1, w - 1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float h0 = __fadd_rn(__fmul_rn(px(r0, cx.s, c), cx.w0), __fmul_rn(px(r0, x1, c), cx.w1));
+        const float h1 = __fadd_rn(__fmul_rn(px(r1, cx.s, c), cx.w0), __fmul_rn(px(r1, x1, c), cx.w1));
+        o[c * plane] = __fadd_rn(__fmul_rn(h0, cy.w0), __fmul_rn(h1, cy.w1));
+    }
+}
+
 }  // namespace dt

@@ -176,14 +176,32 @@ def tf32_residual(w):
     return lo
 
 
+def fp16_split(w, multiplier=1.0):
+    """w fp32 -> (hi, lo) fp16 tensors of w * multiplier (multiplier must be a power of two)."""
+    _need_cuda(w)
+    hi = torch.empty(w.shape, dtype=torch.float16, device=w.device)
+    lo = torch.empty_like(hi)
+    _lib.check(_lib.lib().dt_fp16_split(_p(w.contiguous()), w.numel(), float(multiplier), _p(hi), _p(lo), _stream()), "dt_fp16_split")
+    return hi, lo
+
+
+def weight_multiplier(w):
+    """Power of two that brings max|w| into [2^13, 2^14): the fp16 low half then stays a normal number for every weight
+    within 2^-9 of the largest one."""
+    m = float(w.abs().max())
+    if not (m > 0.0):
+        return 1.0
+    import math
+    return 2.0 ** (13 - math.floor(math.log2(m)))
+
+
 def conv2d_nhwc(x, w_kmajor, scale, shift, kh, kw, pad, stride, w_lo=None, residual=None, up_src=None, relu=False, sigmoid_ch=0,
-                passes=3, force_block_n=0, out=None):
-    """x [N,H,W,Cin] fp32 (channels-last memory), w_kmajor [Cout, kh*kw*Cin] -> y [N,Ho,Wo,Cout]."""
+                passes=3, force_block_n=0, out=None, kind="tf32", range_flag=None):
+    """x [N,H,W,Cin] fp32 (channels-last memory), w_kmajor [Cout, kh*kw*Cin] -> y [N,Ho,Wo,Cout].
+    kind "tf32": 3xTF32 (w_lo = tf32 residual); kind "f16": 3xFP16 on the kind::f16 pipe (weights split here)."""
     _need_cuda(x, w_kmajor)
     N, H, W, Cin = x.shape
     Cout = w_kmajor.size(0)
-    if w_lo is None:
-        w_lo = tf32_residual(w_kmajor)
     Ho = (H + 2 * pad - kh) // stride + 1
     Wo = (W + 2 * pad - kw) // stride + 1
     if out is None:
@@ -191,6 +209,17 @@ def conv2d_nhwc(x, w_kmajor, scale, shift, kh, kw, pad, stride, w_lo=None, resid
     res_mode = 1 if residual is not None else (2 if up_src is not None else 0)
     up_h = up_src.size(1) if up_src is not None else 0
     up_w = up_src.size(2) if up_src is not None else 0
+    if kind == "f16":
+        mult = weight_multiplier(w_kmajor)
+        hi, lo = fp16_split(w_kmajor, mult)
+        sc = (scale / mult).contiguous()
+        ok = _lib.lib().dt_conv2d_nhwc_f16x3(_p(x), N, H, W, Cin, Cin, _p(hi), _p(lo), Cout, kh, kw, pad, stride, _p(sc), _p(shift), _p(residual),
+                                             res_mode, _p(up_src), up_h, up_w, int(relu), int(sigmoid_ch), int(passes), int(force_block_n),
+                                             _p(range_flag), _p(out), Cout, _stream())
+        _lib.check(ok, "dt_conv2d_nhwc_f16x3")
+        return out
+    if w_lo is None:
+        w_lo = tf32_residual(w_kmajor)
     ok = _lib.lib().dt_conv2d_nhwc(_p(x), N, H, W, Cin, Cin, _p(w_kmajor), _p(w_lo), Cout, kh, kw, pad, stride, _p(scale), _p(shift),
                                    _p(residual), res_mode, _p(up_src), up_h, up_w, int(relu), int(sigmoid_ch), int(passes),
                                    int(force_block_n), _p(out), Cout, _stream())

@@ -104,6 +104,18 @@ int dt_segm_paste(const float* masks, const int* classes, int num_mask_classes, 
                   uint8_t* out, dt_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Image pre-processing (the step right before the path).
+ * Replaces: lib/utils/blob.py:57-87 prep_im_for_blob (float32, minus pixel_means, cv2.resize(fx=fy=im_scale, INTER_LINEAR)) fused
+ * with blob.py:27-55 im_list_to_blob (zero-pad to a multiple of the coarsest FPN stride, HWC -> CHW).
+ *   image_hwc    device uint8 [height, width, 3] (BGR, as cv2.imread returns it)
+ *   pixel_means  HOST double[3]; im_scale: the factor prep_im_for_blob computes (target_size / min side, capped by max_size)
+ *   out_height/out_width = cvRound(height * im_scale), cvRound(width * im_scale)  (the size cv2.resize produces)
+ *   blob_chw     device fp32 [3, blob_height, blob_width], zero outside the resized image
+ */
+int dt_prep_image(const uint8_t* image_hwc, int height, int width, const double* pixel_means, double im_scale, int out_height, int out_width,
+                  float* blob_chw, int blob_height, int blob_width, dt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Convolution / GEMM on tcgen05 tensor cores (3xTF32, fp32-accurate), NHWC activations.
  * Replaces the torch.nn.Conv2d / Linear / ConvTranspose2d calls of lib/model/detector.py
  * (:17-27 FPN, :58-59 FC6/FC7, :71-74 mask convs, :89-90 deconv + mask logits, :119-121 RPN, :170-183 trunk).
@@ -112,8 +124,18 @@ int dt_segm_paste(const float* masks, const int* classes, int num_mask_classes, 
  *   y        [N,Ho,Wo,Cout] (Cout % 4 == 0), y = act( conv(x,w)*scale[c] + shift[c] (+ residual) )
  *   res_mode 0 none | 1 residual [N,Ho,Wo,Cout] | 2 nearest-2x-upsampled up_src [N,up_h,up_w,Cout]
  *   relu     0/1 ; sigmoid_ch: channels [0,sigmoid_ch) get a sigmoid ; passes 3 (3xTF32) or 1 (TF32)
+ *   force_block_n 0 = auto | 64 | 128 | 256 | -1 = 128 with 3 rotating accumulators (shortest truncating-accumulate chains)
+ * dt_conv2d_nhwc_f16x3 is the same product on the kind::f16 pipe (twice the tf32 issue rate): w_hi16 / w_lo16 are the fp16 halves of
+ * w * multiplier from dt_fp16_split (multiplier a power of two that keeps the low half a normal fp16 number; the caller folds
+ * 1/multiplier into `scale`); the fp32 activations are split in shared memory.  *range_flag (device int, may be NULL) is set
+ * to 1 if an activation does not fit fp16 (|x| >= 65504); the result is then not meaningful and the tf32 entry must be used.
  */
 int dt_tf32_residual(const float* w, float* w_lo, int64_t n, dt_stream_t stream);
+int dt_fp16_split(const float* w, int64_t n, float multiplier, void* w_hi16, void* w_lo16, dt_stream_t stream);
+int dt_conv2d_nhwc_f16x3(const float* x, int N, int H, int W, int Cin, int x_pix_stride, const void* w_hi16, const void* w_lo16, int Cout,
+                         int kh, int kw, int pad, int stride, const float* scale, const float* shift, const float* residual, int res_mode,
+                         const float* up_src, int up_h, int up_w, int relu, int sigmoid_ch, int passes, int force_block_n, int* range_flag,
+                         float* y, int y_pix_stride, dt_stream_t stream);
 int dt_conv2d_nhwc(const float* x, int N, int H, int W, int Cin, int x_pix_stride, const float* w, const float* w_lo, int Cout,
                    int kh, int kw, int pad, int stride, const float* scale, const float* shift, const float* residual,
                    int res_mode, const float* up_src, int up_h, int up_w, int relu, int sigmoid_ch, int passes, int force_block_n,

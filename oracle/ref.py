@@ -19,6 +19,7 @@ results are bit-identical to the reference run on CPU):
   expand_boxes / segm_results lib/utils/boxes.py:245-261, lib/utils/result_utils.py:170-228  
   resize_linear_f32           cv2.resize(float32, INTER_LINEAR) -- OpenCV's own (non-IPP) algorithm, modules/imgproc/src/resize.cpp
   rle_encode / rle_to_string  pycocotools maskApi.c rleEncode / rleToString (third-party, not installed here)
+  prep_im_for_blob / im_list_to_blob   lib/utils/blob.py:27-87  
 
 Parity pinned: tests/test_oracle.py checks every function here against (a) the
 reference's own modules imported from /root/reference when that tree is
@@ -463,3 +464,63 @@ def segm_results(cls_boxes, masks, ref_boxes, im_h, im_w, num_classes=81, M=14, 
         cls_segms[j] = segms
     assert mask_ind == masks.shape[0]
     return cls_segms
+
+
+# ------------------------------------------------------------------------------------------------ image pre-processing (8f rank 3)
+def resize_linear_f32_scale(src, fx):
+    """cv2.resize(src float32 HxWxC, None, None, fx=fx, fy=fx, INTER_LINEAR): dsize = cvRound(size * fx), coefficients from
+    scale = 1/fx (not src/dst); fx == 0.5 is routed by OpenCV to its area-fast kernel (for C == 3: ((a+b)+c)+d times 0.25f)."""
+    f32 = np.float32
+    src = np.ascontiguousarray(src, dtype=f32)
+    sh, sw = src.shape[:2]
+    w, h = int(np.rint(sw * fx)), int(np.rint(sh * fx))
+    scale = 1.0 / fx
+    if abs(scale - 2.0) < np.finfo(np.float64).eps:
+        a, b, c, d = src[0:2 * h:2, 0:2 * w:2], src[0:2 * h:2, 1:2 * w:2], src[1:2 * h:2, 0:2 * w:2], src[1:2 * h:2, 1:2 * w:2]
+        return ((((a + b).astype(f32) + c).astype(f32) + d).astype(f32) * f32(.25)).astype(f32)
+
+    def axis(dst):
+        f = ((np.arange(dst, dtype=np.float64) + 0.5) * scale - 0.5).astype(f32)
+        s = np.floor(f).astype(np.int64)
+        return s, (f - s.astype(f32)).astype(f32)
+
+    sx, fxw = axis(w)
+    sy, fyw = axis(h)
+    lo = sx < 0
+    fxw = np.where(lo, f32(0), fxw); sx = np.where(lo, 0, sx)
+    hi = sx >= sw - 1
+    fxw = np.where(hi, f32(0), fxw); sx = np.where(hi, sw - 1, sx)
+    a0, a1 = (f32(1) - fxw).astype(f32), fxw
+    sx1 = np.minimum(sx + 1, sw - 1)
+    hb = ((src[:, sx] * a0[None, :, None]).astype(f32) + (src[:, sx1] * a1[None, :, None]).astype(f32)).astype(f32)
+    r0, r1 = np.clip(sy, 0, sh - 1), np.clip(sy + 1, 0, sh - 1)
+    b0, b1 = (f32(1) - fyw).astype(f32), fyw
+    return ((hb[r0] * b0[:, None, None]).astype(f32) + (hb[r1] * b1[:, None, None]).astype(f32)).astype(f32)
+
+
+def prep_im_for_blob(im, pixel_means=(122.7717, 115.9465, 102.9801), target_sizes=(800,), max_size=1333):
+    """lib/utils/blob.py:57-87 with cv2.resize -> resize_linear_f32_scale."""
+    im = im.astype(np.float32, copy=True)
+    im -= list(pixel_means)
+    im_size_min, im_size_max = np.min(im.shape[0:2]), np.max(im.shape[0:2])
+    ims, im_scales = [], []
+    for target_size in target_sizes:
+        im_scale = float(target_size) / float(im_size_min)
+        if np.round(im_scale * im_size_max) > max_size:
+            im_scale = float(max_size) / float(im_size_max)
+        ims.append(resize_linear_f32_scale(im, im_scale))
+        im_scales.append(im_scale)
+    return ims, im_scales
+
+
+def im_list_to_blob(ims, fpn_on=False, fpn_coarsest_stride=32):
+    """lib/utils/blob.py:27-55."""
+    max_shape = np.array([im.shape for im in ims]).max(axis=0)
+    if fpn_on:
+        stride = float(fpn_coarsest_stride)
+        max_shape[0] = int(np.ceil(max_shape[0] / stride) * stride)
+        max_shape[1] = int(np.ceil(max_shape[1] / stride) * stride)
+    blob = np.zeros((len(ims), max_shape[0], max_shape[1], 3), dtype=np.float32)
+    for i, im in enumerate(ims):
+        blob[i, 0:im.shape[0], 0:im.shape[1], :] = im
+    return blob.transpose((0, 3, 1, 2))

@@ -193,7 +193,7 @@ def test_nms_large_properties(dev):
 
 
 # ------------------------------------------------------------------------------- conv / GEMM (tcgen05, 3xTF32)
-def _conv_case(dev, N, Hh, Ww, Cin, Cout, k, pad, stride, res=False, up=False, relu=False, sig=0, passes=3):
+def _conv_case(dev, N, Hh, Ww, Cin, Cout, k, pad, stride, res=False, up=False, relu=False, sig=0, passes=3, kind="tf32", force_block_n=0):
     from detectorch_b200 import ops
     g = torch.Generator().manual_seed(N * 1000 + Hh * 10 + Cin + Cout + k)
     x = torch.randn((N, Hh, Ww, Cin), generator=g)
@@ -214,7 +214,8 @@ def _conv_case(dev, N, Hh, Ww, Cin, Cout, k, pad, stride, res=False, up=False, r
     if sig:
         y[..., :sig] = torch.sigmoid(y[..., :sig])
     got = ops.conv2d_nhwc(x.to(dev), w.reshape(Cout, -1).contiguous().to(dev), sc.to(dev), sh.to(dev), k, k, pad, stride,
-                          residual=R.to(dev) if res else None, up_src=U.to(dev) if up else None, relu=relu, sigmoid_ch=sig, passes=passes)
+                          residual=R.to(dev) if res else None, up_src=U.to(dev) if up else None, relu=relu, sigmoid_ch=sig, passes=passes,
+                          kind=kind, force_block_n=force_block_n)
     err = (got.cpu().double() - y).abs().max().item()
     return err / max(1.0, y.abs().max().item())
 
@@ -225,6 +226,38 @@ def _conv_case(dev, N, Hh, Ww, Cin, Cout, k, pad, stride, res=False, up=False, r
 def test_conv_3xtf32_matches_fp64_within_1e4(dev, case):
     # tolerance: 1e-4 of the tensor's max-abs (BASELINE north_star fp32 parity bar); 3xTF32 measures ~1e-6..1e-5
     assert _conv_case(dev, *case) < 1e-4
+
+
+_CONV_CASES = [(1, 1, 128, 64, 64, 1, 0, 1), (1, 1, 1000, 1024, 408, 1, 0, 1), (1, 20, 30, 64, 128, 3, 1, 1), (2, 25, 38, 256, 256, 3, 1, 1),
+               (1, 50, 76, 256, 128, 1, 0, 2), (2, 25, 38, 128, 64, 1, 0, 2), (5, 14, 14, 256, 256, 3, 1, 1), (1, 1, 300, 12544, 1024, 1, 0, 1)]
+
+
+@pytest.mark.parametrize("case", _CONV_CASES)
+def test_conv_3xf16_matches_fp64_within_1e4(dev, case):
+    """The kind::f16 three-term product (fp16 hi/lo halves of both operands, fp32 accumulate) meets the same fp32 parity bar."""
+    assert _conv_case(dev, *case, kind="f16") < 1e-4
+
+
+def test_conv_f16_epilogues_tiles_and_range_flag(dev):
+    from detectorch_b200 import ops
+    assert _conv_case(dev, 1, 20, 30, 64, 256, 1, 0, 1, res=True, relu=True, kind="f16") < 1e-4
+    assert _conv_case(dev, 2, 13, 19, 128, 64, 3, 1, 1, res=True, relu=True, kind="f16") < 1e-4
+    assert _conv_case(dev, 1, 26, 38, 64, 256, 1, 0, 1, up=True, kind="f16") < 1e-4
+    assert _conv_case(dev, 1, 25, 38, 256, 16, 1, 0, 1, sig=3, kind="f16") < 1e-4
+    assert _conv_case(dev, 5, 14, 14, 256, 256, 3, 1, 1, kind="f16", force_block_n=-1) < 1e-4      # precise 128-wide tile
+    assert _conv_case(dev, 5, 14, 14, 256, 256, 3, 1, 1, kind="f16", force_block_n=128) < 1e-4
+    assert _conv_case(dev, 1, 1, 512, 2048, 256, 1, 0, 1, kind="f16") < 1e-4                         # K = 2048: cta_group::2 variant
+    assert 1e-5 < _conv_case(dev, 1, 1, 256, 1024, 128, 1, 0, 1, passes=1, kind="f16") < 5e-3       # single fp16 pass: not fp32-accurate
+    # fp16 has a 5-bit exponent: an activation of 1e5 raises the range flag, ordinary data does not
+    x = torch.randn((1, 4, 32, 64), device=dev)
+    w = torch.randn((64, 64), device=dev) * 0.1
+    one, zero = torch.ones(64, device=dev), torch.zeros(64, device=dev)
+    flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+    ops.conv2d_nhwc(x, w, one, zero, 1, 1, 0, 1, kind="f16", range_flag=flag)
+    assert int(flag.item()) == 0
+    x[0, 1, 7, 3] = 1.0e5
+    ops.conv2d_nhwc(x, w, one, zero, 1, 1, 0, 1, kind="f16", range_flag=flag)
+    assert int(flag.item()) == 1
 
 
 def test_conv_both_mma_modes(built):
@@ -327,3 +360,27 @@ def test_segm_full_size_and_edges(dev):
     nd = torch.tensor([3], dtype=torch.int32, device=dev)
     c3, s3 = ops.segm_rle(tm[:8], None, tb[:8], im_h, im_w, num_dets=nd)
     assert [len(c) for c in c3[3:]] == [0] * 5 and s3[:3] == strings[:3]
+
+
+# ------------------------------------------------------------------------------------------------ image pre-processing (8f rank 3)
+def test_prep_image_golden_and_full_size(dev):
+    """dt_prep_image == the reference's prep_im_for_blob + im_list_to_blob bit for bit (fixtures generated by the reference with the
+    real cv2), and at the headline size (a 480x640 image -> 3x800x1088 blob) against the oracle; mirror preprocess_sample."""
+    from detectorch_b200.utils import blob as B
+    from detectorch_b200.utils.preprocess_sample import preprocess_sample
+    P = np.load(os.path.join(os.path.dirname(__file__), "golden", "prep_golden.npz"))
+    for i, (h, w, ts, ms) in enumerate(P["cases"]):
+        blob, s = B.image_to_blob(P["im%d" % i], target_size=int(ts), max_size=int(ms), fpn_on=True)
+        assert s == float(P["scale%d" % i])
+        assert np.array_equal(blob.cpu().numpy(), P["blob%d" % i])
+        ims, scales = B.prep_im_for_blob(P["im%d" % i], target_sizes=[int(ts)], max_size=int(ms))
+        assert np.array_equal(B.im_list_to_blob(ims, fpn_on=True).cpu().numpy(), P["blob%d" % i])
+    ref = ref_mod()
+    rng = np.random.RandomState(2)
+    for (h, w) in ((480, 640), (375, 1242), (1600, 2000)):
+        im = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        ims, scales = ref.prep_im_for_blob(im)
+        want = ref.im_list_to_blob(ims, fpn_on=True)
+        sample = preprocess_sample(fpn_on=True)({'image': im, 'dbentry': {'boxes': np.zeros((0, 4), np.float32)}})
+        assert sample['scaling_factors'] == scales[0] and tuple(sample['original_im_size'].tolist()) == (h, w, 3)
+        assert sample['image'].is_cuda and np.array_equal(sample['image'].cpu().numpy(), want)
