@@ -163,9 +163,10 @@ def run_ours(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
+    eng.check_range()      # the kind::f16 conv path raises a device flag if an activation left the fp16 range (never on this workload)
 
     # ---- (B) end to end through the device-facing call with HOST buffers: H2D of the images, D2H of the results
-    res_keys = ["det_boxes", "det_scores", "det_classes", "det_counts", "masks"]
+    res_keys = ["det_boxes", "det_scores", "det_classes", "det_counts", "masks", "range_flag"]
     res_dev = [eng.buffer(k) for k in res_keys]
     res_host = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res_dev] for _ in range(2)]
     h2d_bytes = host[0].numel() * 4
@@ -219,14 +220,16 @@ def run_ours(args):
         conv = [(m, f) for (m, f, st, bn) in prof if bn > 0]
         conv_ms, conv_flops = sum(m for m, _ in conv), sum(f for _, f in conv)
         all_ms = sum(m for (m, _, _, _) in prof)
-        tf32_peak = bf16_peak / 2.0          # kind::tf32 issues at half the kind::f16 rate (B200_PROFILING.md nominal 1.1 vs 2.25 PF)
+        f16_kind = eng.cfg.conv_kind == 0
+        # kind::f16 issues at the bf16 rate; kind::tf32 at half of it (B200_PROFILING.md nominal 2.25 vs 1.1 PF)
+        mma_peak = bf16_peak if f16_kind else bf16_peak / 2.0
         ach = conv_flops / (conv_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "conv_tcgen05_kernel (%d launches/step)" % len(conv), "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": ach / tf32_peak, "traffic": None,
-                "peak_source": "%s bf16_tflops_sustained/2 (tf32 MMA rate is half of bf16)" % which,
-                "executed_tflops": 3.0 * ach, "frac_executed": 3.0 * ach / tf32_peak,
-                "note": "achieved = algorithmic 2*MAC FLOPs of all conv/GEMM launches / their summed CUDA-event time; the kernel executes 3 TF32 MMAs "
-                        "per algorithmic product (3xTF32 fp32 emulation), frac_executed counts those",
+        roof = {"bound": "tensor", "kernel": "conv_tcgen05_kernel (%d launches/step)" % len(conv), "achieved": ach, "peak": mma_peak, "unit": "TFLOP/s",
+                "frac": ach / mma_peak, "traffic": None,
+                "peak_source": "%s bf16_tflops_sustained%s" % (which, " (kind::f16 MMA rate)" if f16_kind else "/2 (tf32 MMA rate is half of bf16)"),
+                "executed_tflops": 3.0 * ach, "frac_executed": 3.0 * ach / mma_peak,
+                "note": "achieved = algorithmic 2*MAC FLOPs of all conv/GEMM launches / their summed CUDA-event time; the kernel executes 3 %s MMAs "
+                        "per algorithmic product (error-compensated hi/lo split, fp32-accurate), frac_executed counts those" % ("fp16" if f16_kind else "TF32"),
                 "share_of_step": conv_ms / all_ms}
         # RoIAlign (box head, 7x7): algorithmic bytes = output write + RoIs (maps are L2 resident)
         roi = [m for (m, f, st, bn) in prof if st == 5]
@@ -244,7 +247,7 @@ def run_ours(args):
         value = total_images / (ms * 1e-3)
         gflop_img = GFLOP_PER_IMAGE if args.arch == "resnet50" else 634.5
         line = {"metric": METRIC if args.arch == "resnet50" else METRIC.replace("R-50", "R-101"), "value": value, "unit": "images/sec", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (%s tensor-core products, fp32 accumulate)" % ("3xFP16 hi/lo" if eng.cfg.conv_kind == 0 else "3xTF32"),
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD if args.arch == "resnet50" else WORKLOAD.replace("R-50", "R-101").replace("configs[2]", "configs[3] model"), "global_batch": BATCH * world, "parallelism": "dp%d (images sharded, no data-path collective)" % world,
                            "l2": "inputs alternate between two 93 MB batches and every step streams ~11 GB of activations (>> 126 MB L2)",

@@ -11,6 +11,8 @@
 #include <vector>
 
 #include "../../include/detectorch_b200.h"
+#include <cuda_fp16.h>
+
 #include "conv_host.cuh"
 #include "detect_ops.cuh"
 #include "roi_align.cuh"
@@ -88,6 +90,40 @@ __global__ void tf32_lo_kernel(const float* __restrict__ w, float* __restrict__ 
         lo[i] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
     }
 }
+// ---- fp16 hi/lo weight halves for the kind::f16 convs (per-matrix power-of-two pre-scale) ----------
+struct MatInfo { unsigned int maxbits; float mult; };
+__global__ void absmax_kernel(const float* __restrict__ w, long long n, MatInfo* __restrict__ info) {
+    unsigned int m = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = max(m, __float_as_uint(w[i]) & 0x7fffffffu);        // non-negative floats order like their bit patterns
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&info->maxbits, m);
+}
+// multiplier = the power of two that brings max|w| into [2^13, 2^14): the fp16 low half of every weight within 2^-9 of the largest
+// one is then a normal number; 1 for an all-zero (or non-finite) matrix
+__global__ void matmult_kernel(MatInfo* __restrict__ info, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int e = (int)((info[i].maxbits >> 23) & 255u) - 127;
+    int pe = 127 + 13 - e;
+    if (info[i].maxbits == 0 || e == 128) pe = 127;
+    pe = pe < 1 ? 1 : (pe > 254 ? 254 : pe);
+    info[i].mult = __uint_as_float((unsigned int)pe << 23);
+}
+__global__ void fp16_split_dev_kernel(const float* __restrict__ w, long long n, const MatInfo* __restrict__ info, __half* __restrict__ hi,
+                                      __half* __restrict__ lo) {
+    const float mult = info->mult;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = w[i] * mult;
+        const __half h = __float2half_rn(v);
+        hi[i] = h;
+        lo[i] = __float2half_rn(v - __half2float(h));
+    }
+}
+__global__ void scale16_kernel(const float* __restrict__ scale, const MatInfo* __restrict__ info, float* __restrict__ dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = scale[i] / info->mult;      // division by a power of two: exact
+}
 inline int grid_for(long long n, int threads = 256) {
     long long g = (n + threads - 1) / threads;
     return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
@@ -119,6 +155,11 @@ struct Op {
     int kind;            // 0 conv, 1 custom lambda index
     ConvLayer conv;
     int fn;              // index into engine fns for kind==1
+    // kind::f16 convs: scale16 = scale / multiplier(matrix) is (re)derived at finalize time
+    const float* scale_src = nullptr;
+    float* scale16 = nullptr;
+    int scale_n = 0;
+    int matrix = -1;
 };
 
 struct Engine;
@@ -154,9 +195,25 @@ struct Engine {
     int num_stage_fns = 0;
     std::vector<StageFn> fns;
 
+    // weight buffer: [fp32 matrices][tf32 residuals][vectors][fp16 hi halves][fp16 lo halves][scale16 arena][matrix info]
+    static constexpr size_t kScale16Floats = 768 * 1024;
+    static constexpr size_t kMaxMatrices = 1024;
+    std::vector<std::pair<size_t, size_t>> matrices;   // (offset, floats) of every weight matrix, ascending
+    size_t scale16_used = 0;
     float* wmat(size_t off) const { return wbase + off; }
     float* wlo(size_t off) const { return wbase + mat_floats + off; }
     float* wvec(size_t off) const { return wbase + 2 * mat_floats + off; }
+    __half* whi16(size_t off) const { return reinterpret_cast<__half*>(wbase + 2 * mat_floats + vec_floats) + off; }
+    __half* wlo16(size_t off) const { return whi16(0) + mat_floats + off; }
+    float* scale16_arena() const { return wbase + 3 * mat_floats + vec_floats; }
+    MatInfo* matinfo() const { return reinterpret_cast<MatInfo*>(scale16_arena() + kScale16Floats); }
+    size_t weight_bytes() const { return (3 * mat_floats + vec_floats + kScale16Floats) * sizeof(float) + kMaxMatrices * sizeof(MatInfo); }
+    int matrix_of(size_t off) const {
+        int m = -1;
+        for (size_t i = 0; i < matrices.size(); ++i)
+            if (matrices[i].first <= off && off < matrices[i].first + matrices[i].second) m = (int)i;
+        return m;
+    }
     template <class T = float>
     T* buf(const std::string& n) {
         auto it = bufs.find(n);
@@ -172,6 +229,7 @@ size_t add_mat(Engine* e, const std::string& name, ParamKind kind, int rows_tota
     if (row_off == 0) {
         s.off = e->mat_floats;
         e->mat_floats += align_up((size_t)rows_total * K, 64);
+        e->matrices.push_back(std::make_pair(s.off, e->mat_floats - s.off));
     }
     e->params[name] = s;
     return s.off;
@@ -350,6 +408,7 @@ void plan_buffers(Engine* e) {
     add_buf(e, "det_v0", {B, (long long)NC * post}, 1); add_buf(e, "det_v1", {B, (long long)NC * post}, 1);
     add_buf(e, "det_boxes", {B, cap, 4}); add_buf(e, "det_scores", {B, cap}); add_buf(e, "det_classes", {B, cap}, 1);
     add_buf(e, "det_roi_idx", {B, cap}, 1); add_buf(e, "det_counts", {B}, 1);
+    add_buf(e, "range_flag", {1}, 1);     // raised by a kind::f16 conv when an activation does not fit fp16
     if (c.use_mask) {
         const long long D = (long long)B * cap;
         add_buf(e, "mask_rois", {D, 5}); add_buf(e, "mask_levels", {D}, 1);
@@ -379,14 +438,33 @@ struct ProgBuilder {
         ConvSpec s;
         memset(&s, 0, sizeof(s));
         s.x = x; s.N = N; s.H = H; s.W = W; s.Cin = c.cin; s.x_pix_stride = xstride;
-        s.w_hi = e->wmat(c.w + w_extra_off); s.w_lo = e->wlo(c.w + w_extra_off);
+        Op op;
         s.Cout = c.cout; s.kh = c.k; s.kw = c.k; s.pad = kpad; s.stride = stride;
-        s.scale = e->wvec(c.scale); s.shift = e->wvec(c.shift);
+        s.shift = e->wvec(c.shift);
+        if (e->cfg.conv_kind == 0) {
+            // kind::f16 three-term product: fp16 halves of w * multiplier(matrix); the multiplier is undone through a per-op scale vector
+            const size_t n16 = align_up((size_t)c.cout, 64);
+            op.matrix = e->matrix_of(c.w + w_extra_off);
+            if (op.matrix < 0 || e->scale16_used + n16 > Engine::kScale16Floats) {
+                ok = false;
+                fprintf(stderr, "[detectorch_b200] engine: scale16 arena / matrix lookup failed for %s\n", wname.c_str());
+                return;
+            }
+            op.scale_src = e->wvec(c.scale); op.scale16 = e->scale16_arena() + e->scale16_used; op.scale_n = c.cout;
+            e->scale16_used += n16;
+            s.kind = KIND_F16X3;
+            s.w_hi = e->whi16(c.w + w_extra_off); s.w_lo = e->wlo16(c.w + w_extra_off);
+            s.scale = op.scale16;
+            s.range_flag = e->buf<int>("range_flag");
+        } else {
+            s.kind = KIND_TF32X3;
+            s.w_hi = e->wmat(c.w + w_extra_off); s.w_lo = e->wlo(c.w + w_extra_off);
+            s.scale = e->wvec(c.scale);
+        }
         s.y = y; s.y_pix_stride = ystride;
         s.out_h = out_h; s.out_w = out_w; s.out_step = out_step; s.out_y0 = oy; s.out_x0 = ox;
         s.residual = res; s.res_pix_stride = c.cout; s.up_src = up; s.up_h = up_h; s.up_w = up_w;
         s.res_mode = res_mode; s.relu = relu ? 1 : 0; s.sigmoid_ch = sigmoid_ch; s.passes = e->cfg.passes; s.force_block_n = force_bn; s.precise = (force_bn == 128) ? 1 : 0;
-        Op op;
         op.stage = stage; op.kind = 0; op.fn = -1;
         {
             const int Ho = (H + 2 * kpad - c.k) / stride + 1, Wo = (W + 2 * kpad - c.k) / stride + 1;
@@ -511,9 +589,19 @@ bool build_program(Engine* e, std::map<std::string, ConvW>* cw) {
         Op op;
         op.stage = ST_TRUNK; op.kind = 0; op.fn = -1;
         op.flops = 2.0 * (double)B * e->H1 * e->W1 * 64.0 * 147.0;
-        e->stem_fused = c.stem_im2col ? false
-                                      : conv_build_stem(e->buf("stem_x4"), B, e->Hp, e->Wp, e->H1, e->W1, e->wmat(sw.w + 64 * 160), e->wlo(sw.w + 64 * 160),
-                                                        e->wvec(sw.scale), e->wvec(sw.shift), e->buf("c1"), c.passes, &op.conv);
+        if (c.stem_im2col) {
+            e->stem_fused = false;
+        } else if (c.conv_kind == 0) {
+            op.matrix = e->matrix_of(sw.w);
+            op.scale_src = e->wvec(sw.scale); op.scale16 = e->scale16_arena() + e->scale16_used; op.scale_n = 64;
+            e->scale16_used += 64;
+            e->stem_fused = conv_build_stem(e->buf("stem_x4"), B, e->Hp, e->Wp, e->H1, e->W1, e->whi16(sw.w + 64 * 160), e->wlo16(sw.w + 64 * 160),
+                                            op.scale16, e->wvec(sw.shift), e->buf("c1"), c.passes, &op.conv, KIND_F16X3, e->buf<int>("range_flag"));
+            if (!e->stem_fused) { op.scale16 = nullptr; op.scale_src = nullptr; }
+        } else {
+            e->stem_fused = conv_build_stem(e->buf("stem_x4"), B, e->Hp, e->Wp, e->H1, e->W1, e->wmat(sw.w + 64 * 160), e->wlo(sw.w + 64 * 160),
+                                            e->wvec(sw.scale), e->wvec(sw.shift), e->buf("c1"), c.passes, &op.conv);
+        }
         if (e->stem_fused) {
             pb.fn(ST_TRUNK, fn_stem_pack);
             e->ops.push_back(op);
@@ -718,7 +806,7 @@ void dt_engine_destroy(dt_engine_t h) { delete reinterpret_cast<Engine*>(h); }
 
 int64_t dt_engine_weight_bytes(dt_engine_t h) {
     Engine* e = reinterpret_cast<Engine*>(h);
-    return (int64_t)((2 * e->mat_floats + e->vec_floats) * sizeof(float));
+    return (int64_t)e->weight_bytes();
 }
 int64_t dt_engine_workspace_bytes(dt_engine_t h) { return (int64_t)reinterpret_cast<Engine*>(h)->ws_bytes; }
 
@@ -732,6 +820,7 @@ int dt_engine_bind(dt_engine_t h, void* weights, void* workspace, dt_stream_t st
     fill_kernel<<<8, 256, 0, st>>>(e->wvec(0), 2048, 1.f);
     DT_CHECK_CUDA(cudaGetLastError());
     e->ops.clear();
+    e->scale16_used = 0;
     e->fns.clear();
     std::map<std::string, ConvW> cw;
     {   // rebuild the (deterministic) table to recover the ConvW offsets
@@ -754,8 +843,27 @@ int dt_engine_finalize_weights(dt_engine_t h, dt_stream_t stream) {
     for (auto& kv : e->params)
         if (!kv.second.loaded) { fprintf(stderr, "[detectorch_b200] engine: parameter %s was never loaded\n", kv.first.c_str()); ++missing; }
     if (missing) return 0;
-    tf32_lo_kernel<<<grid_for((long long)e->mat_floats), 256, 0, (cudaStream_t)stream>>>(e->wmat(0), e->wlo(0), (long long)e->mat_floats);
+    cudaStream_t st = (cudaStream_t)stream;
+    tf32_lo_kernel<<<grid_for((long long)e->mat_floats), 256, 0, st>>>(e->wmat(0), e->wlo(0), (long long)e->mat_floats);
     DT_CHECK_CUDA(cudaGetLastError());
+    if (e->cfg.conv_kind == 0) {
+        // fp16 halves of every matrix, pre-scaled by a per-matrix power of two derived on the device (no host sync)
+        const int nm = (int)e->matrices.size();
+        if ((size_t)nm > Engine::kMaxMatrices) { fprintf(stderr, "[detectorch_b200] engine: too many weight matrices\n"); return 0; }
+        DT_CHECK_CUDA(cudaMemsetAsync(e->matinfo(), 0, nm * sizeof(MatInfo), st));
+        for (int m = 0; m < nm; ++m)
+            absmax_kernel<<<grid_for((long long)e->matrices[m].second), 256, 0, st>>>(e->wmat(e->matrices[m].first), (long long)e->matrices[m].second,
+                                                                                     e->matinfo() + m);
+        matmult_kernel<<<(nm + 255) / 256, 256, 0, st>>>(e->matinfo(), nm);
+        for (int m = 0; m < nm; ++m)
+            fp16_split_dev_kernel<<<grid_for((long long)e->matrices[m].second), 256, 0, st>>>(
+                e->wmat(e->matrices[m].first), (long long)e->matrices[m].second, e->matinfo() + m, e->whi16(e->matrices[m].first),
+                e->wlo16(e->matrices[m].first));
+        for (const Op& op : e->ops)
+            if (op.kind == 0 && op.scale16)
+                scale16_kernel<<<(op.scale_n + 255) / 256, 256, 0, st>>>(op.scale_src, e->matinfo() + op.matrix, op.scale16, op.scale_n);
+        DT_CHECK_CUDA(cudaGetLastError());
+    }
     return 1;
 }
 

@@ -179,14 +179,18 @@ __device__ __forceinline__ uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// Remote arrive on a barrier of another CTA of the cluster.  Default semantics (release at CTA scope), as CUTLASS'
+// ClusterBarrier::arrive does: an explicit .release.cluster makes ptxas emit MEMBAR.ALL.GPU + ERRBAR + CCTL.IVALL (an L1
+// invalidate) in front of every arrive, which serialised the converter warps (ncu: ~1.4k of 9k samples on those fences).  The data
+// this signal publishes was written to shared memory and made visible to the async proxy by fence.proxy.async beforehand.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_LOOP_C:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra WAIT_DONE_C;\n\t"
         "bra WAIT_LOOP_C;\n\t"
         "WAIT_DONE_C:\n\t}" ::"r"(bar),

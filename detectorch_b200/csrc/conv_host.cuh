@@ -227,8 +227,8 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
 // starting at padded pixel 2*ow, so a TMA descriptor whose "pixel" dimension has an OVERLAPPING stride of 8 floats
 // (2 pixels) delivers, per ky, one 32-float K-block per output pixel straight into the swizzled A tile (last 4 floats
 // hit zero weights).  K = 7 x 32.  H uses elementStride 2.
-inline bool conv_build_stem(const float* x4, int B, int Hp, int Wp, int H1, int W1, const float* w_hi, const float* w_lo, const float* scale,
-                            const float* shift, float* y, int passes, ConvLayer* L) {
+inline bool conv_build_stem(const float* x4, int B, int Hp, int Wp, int H1, int W1, const void* w_hi, const void* w_lo, const float* scale,
+                            const float* shift, float* y, int passes, ConvLayer* L, int kind = KIND_TF32X3, int* range_flag = nullptr) {
     memset(&L->p, 0, sizeof(ConvParams));
     ConvParams& p = L->p;
     int wbox, hbox, nbox;
@@ -237,8 +237,15 @@ inline bool conv_build_stem(const float* x4, int B, int Hp, int Wp, int H1, int 
     L->block_n = bn;
     const uint64_t row = (uint64_t)Wp * 16;
     if (!make_tmap_4d(&p.tm_a, x4, 32, W1, Hp, B, 32, row, row * Hp, 32, wbox, hbox * 2, nbox, 1, 2)) return false;
-    if (!make_tmap_2d(&p.tm_bhi, w_hi, 224, 64, 224 * 4, 32, bn / 2)) return false;
-    if (!make_tmap_2d(&p.tm_blo, w_lo, 224, 64, 224 * 4, 32, bn / 2)) return false;
+    if (kind == KIND_F16X3) {
+        if (!make_tmap_2d_f16(&p.tm_bhi, w_hi, 224, 64, 224 * 2, 32, bn / 2)) return false;
+        if (!make_tmap_2d_f16(&p.tm_blo, w_lo, 224, 64, 224 * 2, 32, bn / 2)) return false;
+    } else {
+        if (!make_tmap_2d(&p.tm_bhi, w_hi, 224, 64, 224 * 4, 32, bn / 2)) return false;
+        if (!make_tmap_2d(&p.tm_blo, w_lo, 224, 64, 224 * 4, 32, bn / 2)) return false;
+    }
+    L->kind = kind == KIND_F16X3 ? KIND_F16X3 : KIND_TF32X3;
+    p.range_flag = range_flag;
     const uint64_t ys = 64 * 4;
     if (!make_tmap_4d(&p.tm_d, y, 64, W1, H1, B, ys, ys * W1, ys * W1 * H1, 32, wbox, hbox, nbox)) return false;
     p.scale = scale; p.shift = shift;

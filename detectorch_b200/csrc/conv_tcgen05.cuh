@@ -284,6 +284,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
                     uint8_t* ah = smem_gen + s * Cfg::STAGE_BYTES + Cfg::A_BYTES;
                     uint8_t* al = ah + Cfg::A_BYTES / 2;
                     bool bad = false;
+                    // rows past the TMA box (boxes smaller than 128 pixels) are never written: whatever they hold produces accumulator
+                    // rows that are never stored, but it must not trip the range flag
+                    const bool live_row = ct * 128 < p.a_tile_bytes;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int r = ct, c8 = i;
@@ -302,7 +305,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
                         *reinterpret_cast<uint4*>(ah + off) = *reinterpret_cast<const uint4*>(hh);
                         if (p.passes == 3) *reinterpret_cast<uint4*>(al + off) = *reinterpret_cast<const uint4*>(ll);
                     }
-                    if (bad && p.range_flag) *p.range_flag = 1;
+                    if (bad && live_row && p.range_flag) *p.range_flag = 1;
                     fence_proxy_async_smem();
                 } else if (p.passes == 3) {
                     // A_lo = A - trunc_tf32(A), element-wise, so the swizzled placement is preserved verbatim

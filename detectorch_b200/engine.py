@@ -2,6 +2,7 @@
 Torch only provides the two flat device buffers, the stream and zero-copy views of the named
 engine tensors; every kernel is launched by the C++ side."""
 import ctypes
+import os
 
 import torch
 
@@ -41,7 +42,8 @@ class EngineConfig(ctypes.Structure):
                 ("rpn_min_size", ctypes.c_float), ("num_classes", ctypes.c_int), ("score_thresh", ctypes.c_float),
                 ("det_nms_thresh", ctypes.c_float), ("max_dets", ctypes.c_int), ("det_cap", ctypes.c_int),
                 ("use_mask", ctypes.c_int), ("output_prob", ctypes.c_int), ("emit_full_masks", ctypes.c_int),
-                ("passes", ctypes.c_int), ("precise_mask", ctypes.c_int), ("stem_im2col", ctypes.c_int), ("exact_roialign", ctypes.c_int), ("model_type", ctypes.c_int), ("use_rpn", ctypes.c_int)]
+                ("passes", ctypes.c_int), ("precise_mask", ctypes.c_int), ("stem_im2col", ctypes.c_int), ("exact_roialign", ctypes.c_int), ("model_type", ctypes.c_int), ("use_rpn", ctypes.c_int),
+                ("conv_kind", ctypes.c_int)]
 
 
 _DTYPES = {0: torch.float32, 1: torch.int32, 2: torch.uint8}
@@ -73,7 +75,7 @@ def _bind_engine_api(L):
 class Engine:
     def __init__(self, arch="resnet50", batch=1, height=800, width=1216, pre_nms_top_n=1000, post_nms_top_n=1000,
                  rpn_nms_thresh=0.7, rpn_min_size=0.0, num_classes=81, score_thresh=0.05, det_nms_thresh=0.5, max_dets=100,
-                 det_cap=100, use_mask=True, output_prob=True, emit_full_masks=False, passes=3, precise_mask=True, stem_im2col=False, exact_roialign=False, model="fpn", use_rpn=True, device="cuda:0"):
+                 det_cap=100, use_mask=True, output_prob=True, emit_full_masks=False, passes=3, precise_mask=True, stem_im2col=False, exact_roialign=False, model="fpn", use_rpn=True, conv_kind=None, device="cuda:0"):
         if not torch.cuda.is_available():
             raise RuntimeError("detectorch_b200.Engine needs a CUDA device (no CPU fallback)")
         self.L = _lib.lib()
@@ -92,6 +94,11 @@ class Engine:
         cfg.exact_roialign = int(exact_roialign)
         cfg.model_type = 1 if model == "c4" else 0
         cfg.use_rpn = int(use_rpn)
+        if conv_kind is None:
+            conv_kind = os.environ.get("DT_CONV_KIND", "f16")
+        if conv_kind not in ("f16", "tf32"):
+            raise ValueError("conv_kind must be 'f16' or 'tf32'")
+        cfg.conv_kind = 0 if conv_kind == "f16" else 1
         self.cfg = cfg
         self.h = self.L.dt_engine_create(ctypes.byref(cfg))
         if not self.h:
@@ -160,6 +167,14 @@ class Engine:
                 raise RuntimeError("image shape %s does not match the engine (%d,3,%d,%d)" % (tuple(image.shape), self.cfg.batch, self.cfg.height, self.cfg.width))
             ptr = image.data_ptr()
         _lib.check(self.L.dt_engine_run(self.h, ptr, float(scaling_factor), int(first), int(last), self._stream()), "dt_engine_run")
+
+    def check_range(self):
+        """kind::f16 convs raise a device flag when an activation does not fit fp16 (|x| >= 65504).  Synchronises; raises if set."""
+        f = self.buffer("range_flag")
+        if int(f.item()) != 0:
+            f.zero_()
+            raise FloatingPointError("detectorch_b200: an activation exceeded the fp16 range of the kind::f16 convolution path; "
+                                     "build the Engine with conv_kind='tf32' for this model / input")
 
     def set_original_size(self, h, w):
         self.L.dt_engine_set_original_size(self.h, float(h), float(w))

@@ -216,6 +216,7 @@ class detector(torch.nn.Module):
             self._activate(eng, sf)
             eng.run(image, sf, ST_TRUNK, ST_BOX_HEAD)
             n = int(eng.buffer("roi_counts")[0].item())
+            eng.check_range()
             feats = [eng.buffer("P%d" % l).permute(0, 3, 1, 2) for l in (2, 3, 4, 5)]     # NCHW-shaped views of the NHWC maps
         else:
             if self.use_rpn_head:
@@ -223,6 +224,7 @@ class detector(torch.nn.Module):
                 self._activate(eng, sf)
                 eng.run(image, sf, ST_TRUNK, ST_BOX_HEAD)
                 n = int(eng.buffer("roi_counts")[0].item())
+                eng.check_range()
             else:
                 if rois is None:
                     raise RuntimeError("Fast R-CNN needs pre-computed proposals (eval_fast.ipynb passes batch['rois'])")
@@ -239,6 +241,7 @@ class detector(torch.nn.Module):
                 er[0, :n, 1:5] = r.to(eng.device)
                 eng.buffer("roi_counts")[0] = n
                 eng.run(None, sf, ST_ROI_BOX, ST_BOX_HEAD)
+                eng.check_range()
             feats = eng.buffer("C4").permute(0, 3, 1, 2)
         cls_score = eng.buffer("cls_prob")[:n]
         bbox_pred = eng.buffer("bbox_pred")[:n]

@@ -172,6 +172,9 @@ typedef struct dt_engine_config {
                                     0 = separable / FMA fast path (fp32 re-association only, ~1e-7 relative) */
     int model_type;              /* 0 = R-50/101-FPN + RPN (+ '1up4convs' mask head); 1 = R-50/101-C4 (res5 head, 'upshare' mask head) */
     int use_rpn;                 /* C4 only: 1 = Faster/Mask R-CNN (single-level RPN), 0 = Fast R-CNN (caller fills the `rois` buffer) */
+    int conv_kind;               /* 0 = three-term product on the kind::f16 pipe (fp16 hi/lo halves, default: twice the tf32 issue rate; an
+                                    activation >= 65504 raises the int32 buffer "range_flag"), 1 = 3xTF32 (no range limit).  The 7x7 stem
+                                    always runs 3xTF32. */
 } dt_engine_config;
 
 typedef void* dt_engine_t;

@@ -33,13 +33,15 @@ def acc():
         print("ACC N%d %dx%d Cin%d Cout%d k%d  tf32 %.2e  f16 %.2e" % (N, H, W, Cin, Cout, k, out["tf32"], out["f16"]), flush=True)
 
 
-def timing():
+def timing(only=None):
     shapes = [("P2 3x3 256->256 200x304", 8, 200, 304, 256, 256, 3, 1, 1, 0), ("C4 3x3 256->256 50x76", 8, 50, 76, 256, 256, 3, 1, 1, 0),
               ("C4 1x1 1024->256", 8, 50, 76, 1024, 256, 1, 0, 1, 0), ("C4 1x1 256->1024", 8, 50, 76, 256, 1024, 1, 0, 1, 0),
               ("C2 3x3 64->64 200x304", 8, 200, 304, 64, 64, 3, 1, 1, 0), ("C2 1x1 64->256", 8, 200, 304, 64, 256, 1, 0, 1, 0),
               ("C3 3x3 128->128 100x152", 8, 100, 152, 128, 128, 3, 1, 1, 0), ("mask 3x3 256->256 precise", 800, 14, 14, 256, 256, 3, 1, 1, -1),
               ("mask 3x3 256->256 128 plain", 800, 14, 14, 256, 256, 3, 1, 1, 128), ("FC6 12544->1024", 1, 1, 8000, 12544, 1024, 1, 0, 1, 0)]
     flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)
+    if only is not None:
+        shapes = [shapes[i] for i in only]
     for (name, N, H, W, Cin, Cout, k, pad, stride, fbn) in shapes:
         x = torch.randn((N, H, W, Cin), device=dev)
         w = torch.randn((Cout, k * k * Cin), device=dev) * 0.02
@@ -82,3 +84,5 @@ if __name__ == "__main__":
         acc()
     if "timing" in which:
         timing()
+    if "one" in which:
+        timing(only=[1, 2])
