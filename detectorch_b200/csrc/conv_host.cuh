@@ -134,9 +134,10 @@ inline void choose_box(int Wo, int Ho, int N, int max_w, int* wbox, int* hbox, i
     *wbox = bw; *hbox = bh; *nbox = bn;
 }
 
-// MMA mode per layer.  cta_group::2 (each SM keeps half of the weight tile, 3 instead of 2 TMA stages) measured 3-10 % faster on
-// the long-K, 256-wide layers and 15-55 % slower on the short-K / narrow ones (extra cluster-scope barrier traffic per k-block),
-// so it is used only where it wins.  DT_CONV_MMA=1sm|2sm forces one mode everywhere (tests exercise both).
+// MMA mode per layer.  cta_group::2 (each SM keeps half of the weight tile: smaller stages, half the B-operand ingest and shared-memory
+// reads per SM) measured 1-22 % faster on every 128- and 256-wide layer once the cluster-scope fences were gone from the per-k-block
+// signalling; the 64-wide layers (stem, 64-channel stage, RPN heads) are a wash or up to 5 % slower, so they stay on 1-SM MMAs with
+// multicast weights.  DT_CONV_MMA=1sm|2sm forces one mode everywhere (tests exercise both).
 inline bool conv_use_two_sm(int block_n, int num_kb) {
     static int v = -1;
     if (v < 0) {
@@ -145,7 +146,14 @@ inline bool conv_use_two_sm(int block_n, int num_kb) {
     }
     if (v == 1) return false;
     if (v == 2) return true;
-    return block_n == 256 && num_kb >= 32;
+    (void)num_kb;
+    return block_n > 64;
+}
+
+inline bool conv_merge_acc(int num_kb) {
+    static int thr = -1;
+    if (thr < 0) { const char* e = getenv("DT_CONV_MERGE_KB"); thr = e ? atoi(e) : 16; }
+    return num_kb <= thr;
 }
 
 // Persistent launch geometry: work items = (pairs of M-tiles) x (N-tiles); one 2-CTA cluster per SM pair (74 on B200),
@@ -217,7 +225,9 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
     p.a_tile_bytes = wbox * hbox * nbox * 128;
     p.relu = s.relu; p.sigmoid_ch = s.sigmoid_ch; p.res_mode = s.res_mode;
     p.passes = s.passes == 1 ? 1 : 3;
-    L->nmain = (bn == 64) ? 3 : ((bn == 128 && s.precise) ? 3 : 1);
+    // 256-wide tiles: (main + cross) accumulators fill the 512 TMEM columns, so the epilogue cannot overlap the next tile; layers with
+    // K <= 512 (where the epilogue is as long as the MMAs, and the accumulation chains are short) use one merged accumulator instead
+    L->nmain = (bn == 64) ? 3 : ((bn == 128 && s.precise) ? 3 : ((bn == 256 && conv_merge_acc(K / 32)) ? 0 : 1));
     finish_grid(L, ceil_div(s.Cout, bn));
     return true;
 }
@@ -279,7 +289,7 @@ inline cudaError_t conv_launch_sm(const ConvLayer& L, cudaStream_t stream) {
     switch (L.block_n) {
         case 64: return conv_launch_cfg<64, 3, TWO, KIND>(L, stream);
         case 128: return L.nmain == 3 ? conv_launch_cfg<128, 3, TWO, KIND>(L, stream) : conv_launch_cfg<128, 1, TWO, KIND>(L, stream);
-        case 256: return conv_launch_cfg<256, 1, TWO, KIND>(L, stream);
+        case 256: return L.nmain == 0 ? conv_launch_cfg<256, 0, TWO, KIND>(L, stream) : conv_launch_cfg<256, 1, TWO, KIND>(L, stream);
         default: return cudaErrorInvalidValue;
     }
 }

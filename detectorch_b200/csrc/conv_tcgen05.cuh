@@ -37,8 +37,8 @@
 //               swizzled smem -> TMA store, 32-channel chunks (even chunks group 0, odd chunks group 1), each group with
 //               its own 16 KB staging slot that is NOT aliased with the pipeline, so the producer / converter / MMA warps
 //               run ahead into the next tile while a tile drains.
-// TMEM holds NMAIN rotating main-term accumulators + 1 cross-term accumulator per tile, double-buffered
-// when two tiles fit in the 512 columns.
+// TMEM holds NMAIN rotating main-term accumulators + 1 cross-term accumulator per tile (NMAIN == 0: a single accumulator for
+// both, used by the short-K 256-wide layers), double-buffered when two tiles fit in the 512 columns.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -248,8 +248,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
                         // the running sum (a systematic shrink of ~0.18 * steps * 2^-23).  Two measures keep the chains short:
                         //  * the two cross terms (~2^-11 of the main term) go to their own accumulator,
                         //  * the main term rotates over NMAIN accumulators by k-block (summed with RN adds in the epilogue).
-                        const uint32_t acc_main = acc0 + (uint32_t)((kb % NMAIN) * BLOCK_N);
-                        const uint32_t main_flag = (kb >= NMAIN || k != 0) ? 1u : 0u;
+                        // NMAIN == 0: short-K layers keep everything in ONE accumulator, which leaves room to double-buffer a
+                        // 256-wide tile (the epilogue of tile i then overlaps the MMAs of tile i+1)
+                        constexpr int NM = NMAIN == 0 ? 1 : NMAIN;
+                        const uint32_t acc_main = acc0 + (uint32_t)((kb % NM) * BLOCK_N);
+                        const uint32_t main_flag = NMAIN == 0 ? ((p.passes == 3 || (kb | k) != 0) ? 1u : 0u) : ((kb >= NMAIN || k != 0) ? 1u : 0u);
                         if (p.passes == 3) {
                             const uint32_t acc_x = acc0 + (uint32_t)(NMAIN * BLOCK_N);
                             mma(acc_x, dal + koff, dbh + koff, (kb | k) != 0);
