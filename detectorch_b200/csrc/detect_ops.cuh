@@ -143,6 +143,28 @@ __device__ __forceinline__ float4 clip_box(float4 b, float wmax, float hmax) {  
     return b;
 }
 
+// exclusive prefix of a per-thread count over the block (all threads must call); *total receives the block total.  scratch: 33 ints
+__device__ __forceinline__ int block_rank_count(int cnt, int* scratch, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    __syncthreads();
+    if (lane == 31) scratch[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int x = lane < nw ? scratch[lane] : 0;
+        int w = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += u; }
+        scratch[lane] = w - x;
+        if (lane == 31) scratch[32] = w;
+    }
+    __syncthreads();
+    *total = scratch[32];
+    return scratch[warp] + incl - cnt;
+}
+
 // block-wide ordered compaction helper: returns the exclusive rank of `flag` among threads of this block
 // sweep (all threads must call); *total receives the block total.  scratch: 33 ints of shared memory.
 __device__ __forceinline__ int block_rank(bool flag, int* scratch, int* total) {
@@ -205,72 +227,123 @@ static __global__ void __launch_bounds__(1024) rpn_proposals_kernel(const __grid
     int* v1 = P.v1 + (size_t)b * P.ws_per_image + lv.ws_off;
     const float* base = lv.rpn_out + (size_t)b * lv.H * lv.W * lv.ch_stride;
     // 1. keys in (H,W,A) order (generate_proposals.py:64,72)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int a = i % lv.A, cell = i / lv.A;
-        k0[i] = float_desc_key(base[(size_t)cell * lv.ch_stride + a]);
-        v0[i] = i;
-    }
-    __syncthreads();
     // 2. top-K by descending score (:77-86).  A full sort of ~180k keys by one CTA costs >1 ms, so first narrow the set
     //    with a two-level 11+11-bit radix select on the key (exact: every key below the boundary sub-bin plus the whole
     //    boundary sub-bin is kept, in index order), then stable-sort only those candidates.
+    //    The passes over the level are latency-bound (one CTA): every thread keeps 4 independent loads in flight.
     const int K = (P.pre_nms <= 0 || P.pre_nms >= n) ? n : P.pre_nms;
     const int* vs = v0;                 // sorted anchor indices end up here
     bool narrowed = false;
-    if (n > 4 * K && n > 8192) {
-        uint32_t* h1 = hist;            // 2048 bins
-        uint32_t* h2 = hist + 2048;     // 2048 bins
-        __shared__ uint32_t sel[4];     // b1, c1, b2, count
+    const bool select = n > 4 * K && n > 8192;
+    uint32_t* h1 = hist;                // 2048 bins
+    uint32_t* h2 = hist + 2048;         // 2048 bins
+    __shared__ uint32_t sel[4];         // b1, c1, b2, count
+    if (select) {
         for (int i = threadIdx.x; i < 4096; i += blockDim.x) hist[i] = 0;
         __syncthreads();
-        // objectness scores cluster in a few exponent bins: aggregate equal digits inside the warp before touching shared memory
-        for (int base_i = 0; base_i < n; base_i += blockDim.x) {
-            const int i = base_i + threadIdx.x;
-            const bool valid = i < n;
-            const unsigned act = __ballot_sync(0xffffffffu, valid);
-            if (valid) {
-                const uint32_t d = k0[i] >> 21;
-                const unsigned m = __match_any_sync(act, d);
-                if ((m & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&h1[d], (uint32_t)__popc(m));
+    }
+    for (int base_i = 0; base_i < n; base_i += 4 * blockDim.x) {
+        uint32_t k[4];
+        bool valid[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = base_i + j * blockDim.x + threadIdx.x;
+            valid[j] = i < n;
+            k[j] = 0u;
+            if (valid[j]) {
+                const int a = i % lv.A, cell = i / lv.A;
+                k[j] = float_desc_key(base[(size_t)cell * lv.ch_stride + a]);
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t c = 0, b = 0;
-            for (; b < 2048; ++b) { if (c + h1[b] >= (uint32_t)K) break; c += h1[b]; }
-            sel[0] = b; sel[1] = c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = base_i + j * blockDim.x + threadIdx.x;
+            if (valid[j]) { k0[i] = k[j]; v0[i] = i; }
+            if (select) {
+                // objectness scores cluster in a few exponent bins: aggregate equal digits inside the warp before touching shared memory
+                const unsigned act = __ballot_sync(0xffffffffu, valid[j]);
+                if (valid[j]) {
+                    const uint32_t d = k[j] >> 21;
+                    const unsigned m = __match_any_sync(act, d);
+                    if ((m & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&h1[d], (uint32_t)__popc(m));
+                }
+            }
         }
+    }
+    __syncthreads();
+    // first bin b with c + h[b] >= K (c = keys in the bins before it), by warp 0: 64 bins per lane, warp prefix, serial scan of one lane's bins
+    auto find_bin = [&](const uint32_t* h, uint32_t c0, uint32_t* out_bin, uint32_t* out_c) {
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            uint32_t sum = 0;
+            for (int t = 0; t < 64; ++t) sum += h[lane * 64 + t];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const uint32_t excl = c0 + incl - sum;
+            const bool hit = excl + sum >= (uint32_t)K;            // the crossing lies in or before this lane's bins
+            const unsigned hits = __ballot_sync(0xffffffffu, hit);
+            if (hits == 0) { if (lane == 0) { *out_bin = 2048; *out_c = c0 + __shfl_sync(0xffffffffu, incl, 31); } }
+            else if (lane == __ffs(hits) - 1) {
+                uint32_t c = excl, bb = (uint32_t)lane * 64;
+                for (; bb < (uint32_t)lane * 64 + 64; ++bb) { if (c + h[bb] >= (uint32_t)K) break; c += h[bb]; }
+                *out_bin = bb; *out_c = c;
+            }
+        }
+    };
+    if (select) {
+        find_bin(h1, 0u, &sel[0], &sel[1]);
         __syncthreads();
         const uint32_t b1 = sel[0], c1 = sel[1];
-        for (int base_i = 0; base_i < n; base_i += blockDim.x) {
-            const int i = base_i + threadIdx.x;
-            const uint32_t k = i < n ? k0[i] : 0u;
-            const bool valid = (i < n) && ((k >> 21) == b1);
-            const unsigned act = __ballot_sync(0xffffffffu, valid);
-            if (valid) {
-                const uint32_t d = (k >> 10) & 2047u;
-                const unsigned m = __match_any_sync(act, d);
-                if ((m & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&h2[d], (uint32_t)__popc(m));
+        for (int base_i = 0; base_i < n; base_i += 4 * blockDim.x) {
+            uint32_t k[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = base_i + j * blockDim.x + threadIdx.x;
+                k[j] = i < n ? k0[i] : 0xffffffffu;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = base_i + j * blockDim.x + threadIdx.x;
+                const bool valid = (i < n) && ((k[j] >> 21) == b1);
+                const unsigned act = __ballot_sync(0xffffffffu, valid);
+                if (valid) {
+                    const uint32_t d = (k[j] >> 10) & 2047u;
+                    const unsigned m = __match_any_sync(act, d);
+                    if ((m & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&h2[d], (uint32_t)__popc(m));
+                }
             }
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t c = c1, b = 0;
-            for (; b < 2048; ++b) { if (c + h2[b] >= (uint32_t)K) break; c += h2[b]; }
-            sel[2] = b; sel[3] = c + (b < 2048 ? h2[b] : 0);
-        }
+        find_bin(h2, c1, &sel[2], &sel[3]);
+        __syncthreads();
+        if (threadIdx.x == 0 && sel[2] < 2048u) sel[3] += h2[sel[2]];
         __syncthreads();
         const uint32_t b2 = sel[2], total = sel[3];
         if (total <= 8192u) {
+            // ordered compaction: a thread owns 4 consecutive indices, one block scan per 4096 keys
             int m = 0;
-            for (int base_i = 0; base_i < n; base_i += blockDim.x) {
-                const int i = base_i + threadIdx.x;
-                uint32_t k = 0;
-                bool f = false;
-                if (i < n) { k = k0[i]; const uint32_t d1 = k >> 21; f = (d1 < b1) || (d1 == b1 && ((k >> 10) & 2047u) <= b2); }
+            for (int base_i = 0; base_i < n; base_i += 4 * blockDim.x) {
+                const int i0 = base_i + 4 * threadIdx.x;
+                uint32_t k[4];
+                bool f[4];
+                int cnt = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + j;
+                    k[j] = i < n ? k0[i] : 0xffffffffu;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t d1 = k[j] >> 21;
+                    f[j] = (i0 + j < n) && ((d1 < b1) || (d1 == b1 && ((k[j] >> 10) & 2047u) <= b2));
+                    cnt += f[j] ? 1 : 0;
+                }
                 int tot;
-                const int r = block_rank(f, scratch, &tot);
-                if (f) { k1[m + r] = k; v1[m + r] = i; }
+                int r = m + block_rank_count(cnt, scratch, &tot);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (f[j]) { k1[r] = k[j]; v1[r] = i0 + j; ++r; }
                 m += tot;
             }
             __syncthreads();

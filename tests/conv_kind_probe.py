@@ -86,3 +86,5 @@ if __name__ == "__main__":
         timing()
     if "one" in which:
         timing(only=[1, 2])
+    if "mask" in which:
+        timing(only=[7])
