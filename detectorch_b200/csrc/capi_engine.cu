@@ -250,6 +250,8 @@ void build_param_table(Engine* e, std::map<std::string, ConvW>* cw) {
     // shared "ones" scale vector for bias-only convs (max Cout 2048)
     size_t ones = e->vec_floats; e->vec_floats += 2048;
     (*cw)["__ones"] = ConvW{0, ones, 0, 2048, 0, 0};
+    size_t zeros = e->vec_floats; e->vec_floats += 2048;     // zero shift vector for the second half of a K-split convolution
+    (*cw)["__zeros"] = ConvW{0, 0, zeros, 2048, 0, 0};
     // stem
     {
         ConvW c; c.cout = 64; c.cin = 160; c.k = 1;
@@ -433,14 +435,15 @@ struct ProgBuilder {
     void conv(int stage, const std::string& wname, const float* x, int N, int H, int W, int xstride, float* y, int ystride, int kpad,
               int stride, bool relu, int res_mode = RES_NONE, const float* res = nullptr, const float* up = nullptr, int up_h = 0,
               int up_w = 0, int sigmoid_ch = 0, size_t w_extra_off = 0, int out_h = 0, int out_w = 0, int out_step = 0, int oy = 0,
-              int ox = 0, int force_bn = 0) {
+              int ox = 0, int force_bn = 0, int tap0 = 0, int ntaps = 0, bool zero_shift = false) {
         const ConvW& c = (*cw)[wname];
         ConvSpec s;
         memset(&s, 0, sizeof(s));
         s.x = x; s.N = N; s.H = H; s.W = W; s.Cin = c.cin; s.x_pix_stride = xstride;
         Op op;
         s.Cout = c.cout; s.kh = c.k; s.kw = c.k; s.pad = kpad; s.stride = stride;
-        s.shift = e->wvec(c.shift);
+        s.shift = zero_shift ? e->wvec((*cw)["__zeros"].shift) : e->wvec(c.shift);
+        s.tap0 = tap0; s.ntaps = ntaps;
         if (e->cfg.conv_kind == 0) {
             // kind::f16 three-term product: fp16 halves of w * multiplier(matrix); the multiplier is undone through a per-op scale vector
             const size_t n16 = align_up((size_t)c.cout, 64);
@@ -470,7 +473,7 @@ struct ProgBuilder {
             const int Ho = (H + 2 * kpad - c.k) / stride + 1, Wo = (W + 2 * kpad - c.k) / stride + 1;
             const double cin_alg = (wname == "stem") ? 147.0 : (double)c.cin;   // the stem K is zero-padded 147 -> 160
             const double cout_alg = (wname == "rpn.head") ? 15.0 : (wname == "head") ? 5.0 * e->cfg.num_classes : (wname == "mask_logits") ? (double)e->cfg.num_classes : (double)c.cout;
-            op.flops = 2.0 * (double)N * Ho * Wo * cout_alg * cin_alg * c.k * c.k;
+            op.flops = 2.0 * (double)N * Ho * Wo * cout_alg * cin_alg * (ntaps > 0 ? ntaps : c.k * c.k);
         }
         if (!conv_build(s, &op.conv)) { ok = false; fprintf(stderr, "[detectorch_b200] engine: conv_build failed for %s\n", wname.c_str()); }
         e->ops.push_back(op);
@@ -721,16 +724,26 @@ bool build_program(Engine* e, std::map<std::string, ConvW>* cw) {
     // ---- mask head (detector.py:99-112)
     if (c.use_mask) {
         const int D = B * c.det_cap, MN = (int)align_up((size_t)NC, 4);
-        // precise_mask: 128-wide tiles leave TMEM room for 3 rotating main accumulators (3x shorter truncating
-        // accumulation chains) on the layers that feed the mask logits, the tensor with the tightest parity bar
-        const int mbn = c.precise_mask ? 128 : 0;
+        // The mask logits carry the tightest parity bar (1e-4 absolute) and sit behind four K = 2304 convolutions, where the tensor
+        // core's truncating fp32 accumulate is the error floor.  precise_mask shortens the chains by SPLITTING K: each 3x3 convolution
+        // runs as two launches over filter taps [0,5) and [5,9); the second adds the first's fp32 result in its epilogue (RES_TILE on the
+        // output buffer itself, round-to-nearest) before the ReLU.  That halves the error like the former 128-wide / 3-accumulator
+        // tiles did, but keeps the 256-wide 2-SM tiles (converted A tiles are shared by all 256 output channels): 2 x ~205 us instead
+        // of 640 us per layer.  precise_mask = 2 selects the old 128-wide rotating-accumulator tiles.
+        const int mbn = c.precise_mask == 2 ? 128 : 0;
         pb.fn(ST_MASK_ROIS, fn_mask_rois);
         pb.fn(ST_MASK_ROI_FEAT, fn_mask_roi_feat);
         const float* mx = e->buf("mask_feat");
         for (int i = 1; i <= 4; ++i) {
-            pb.conv(ST_MASK_HEAD, "mask_head.conv_head.fcn" + std::to_string(i), mx, D, 14, 14, 256, e->buf("mask_c" + std::to_string(i)), 256, 1, 1, true,
-                    RES_NONE, nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, mbn);
-            mx = e->buf("mask_c" + std::to_string(i));
+            const std::string wn = "mask_head.conv_head.fcn" + std::to_string(i);
+            float* my = e->buf("mask_c" + std::to_string(i));
+            if (c.precise_mask == 1) {
+                pb.conv(ST_MASK_HEAD, wn, mx, D, 14, 14, 256, my, 256, 1, 1, false, RES_NONE, nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 5);
+                pb.conv(ST_MASK_HEAD, wn, mx, D, 14, 14, 256, my, 256, 1, 1, true, RES_TILE, my, nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 5, 4, true);
+            } else {
+                pb.conv(ST_MASK_HEAD, wn, mx, D, 14, 14, 256, my, 256, 1, 1, true, RES_NONE, nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, mbn);
+            }
+            mx = my;
         }
         for (int ij = 0; ij < 4; ++ij)     // ConvTranspose2d(2, stride 2) == 4 GEMMs scattered on the 2x grid
             pb.conv(ST_MASK_HEAD, "deconv", mx, D, 14, 14, 256, e->buf("mask_up"), 256, 0, 1, true, RES_NONE, nullptr, nullptr, 0, 0, 0,
@@ -818,6 +831,7 @@ int dt_engine_bind(dt_engine_t h, void* weights, void* workspace, dt_stream_t st
     DT_CHECK_CUDA(cudaMemsetAsync(weights, 0, (2 * e->mat_floats + e->vec_floats) * sizeof(float), st));
     // the shared all-ones scale vector sits at the start of the vector region
     fill_kernel<<<8, 256, 0, st>>>(e->wvec(0), 2048, 1.f);
+    if (e->cfg.model_type != 1) fill_kernel<<<8, 256, 0, st>>>(e->wvec(2048), 2048, 0.f);
     DT_CHECK_CUDA(cudaGetLastError());
     e->ops.clear();
     e->scale16_used = 0;

@@ -113,6 +113,7 @@ struct ConvSpec {
     const float* residual; int res_pix_stride;    // RES_TILE: same geometry as the (plain) output
     const float* up_src; int up_h, up_w;          // RES_UPSAMPLE2X
     int res_mode, relu, sigmoid_ch, passes;
+    int tap0, ntaps;                              // K-split: only filter taps [tap0, tap0+ntaps) (ntaps == 0: all kh*kw)
     int force_block_n;                            // 0 = auto
     int precise;                                  // BLOCK_N == 128 only: 3 rotating accumulators instead of TMEM double-buffering
 };
@@ -218,6 +219,8 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
     p.up_src = s.up_src; p.up_h = s.up_h; p.up_w = s.up_w;
     p.cin_blocks = s.Cin / 32;
     p.kh = s.kh; p.kw = s.kw; p.pad_w = p.pad_h = s.pad; p.stride_w = p.stride_h = s.stride;
+    p.tap0 = s.ntaps > 0 ? s.tap0 : 0; p.ntaps = s.ntaps > 0 ? s.ntaps : s.kh * s.kw;
+    if (p.tap0 < 0 || p.tap0 + p.ntaps > s.kh * s.kw) { fprintf(stderr, "[detectorch_b200] conv_build: bad tap range\n"); return false; }
     p.tiles_w = ceil_div(Wo, wbox); p.tiles_h = ceil_div(Ho, hbox); p.tiles_n = ceil_div(s.N, nbox);
     p.wbox = wbox; p.hbox = hbox; p.nbox = nbox;
     p.wo = Wo; p.ho = Ho; p.nimg = s.N;
@@ -227,7 +230,7 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
     p.passes = s.passes == 1 ? 1 : 3;
     // 256-wide tiles: (main + cross) accumulators fill the 512 TMEM columns, so the epilogue cannot overlap the next tile; layers with
     // K <= 512 (where the epilogue is as long as the MMAs, and the accumulation chains are short) use one merged accumulator instead
-    L->nmain = (bn == 64) ? 3 : ((bn == 128 && s.precise) ? 3 : ((bn == 256 && conv_merge_acc(K / 32)) ? 0 : 1));
+    L->nmain = (bn == 64) ? 3 : ((bn == 128 && s.precise) ? 3 : ((bn == 256 && conv_merge_acc(p.ntaps * p.cin_blocks)) ? 0 : 1));
     finish_grid(L, ceil_div(s.Cout, bn));
     return true;
 }
@@ -259,7 +262,7 @@ inline bool conv_build_stem(const float* x4, int B, int Hp, int Wp, int H1, int 
     const uint64_t ys = 64 * 4;
     if (!make_tmap_4d(&p.tm_d, y, 64, W1, H1, B, ys, ys * W1, ys * W1 * H1, 32, wbox, hbox, nbox)) return false;
     p.scale = scale; p.shift = shift;
-    p.cin_blocks = 1; p.kh = 7; p.kw = 1;
+    p.cin_blocks = 1; p.kh = 7; p.kw = 1; p.tap0 = 0; p.ntaps = 7;
     p.pad_w = 0; p.pad_h = 0; p.stride_w = 1; p.stride_h = 2;
     p.tiles_w = ceil_div(W1, wbox); p.tiles_h = ceil_div(H1, hbox); p.tiles_n = ceil_div(B, nbox);
     p.wbox = wbox; p.hbox = hbox; p.nbox = nbox;

@@ -48,6 +48,9 @@ namespace dt {
 
 enum ConvResidualMode { RES_NONE = 0, RES_TILE = 1, RES_UPSAMPLE2X = 2 };
 enum ConvKind { KIND_TF32X3 = 0, KIND_F16X3 = 1 };
+#ifndef DT_CONV_WARPS_NARROW
+#define DT_CONV_WARPS_NARROW 4
+#endif
 
 struct ConvParams {
     CUtensorMap tm_a;      // 4D {C, W, H, N} over the NHWC input (elementStrides carry the conv stride)
@@ -61,6 +64,7 @@ struct ConvParams {
     int up_h, up_w;
     int cin_blocks;        // Cin / 32
     int kh, kw;
+    int tap0, ntaps;       // this launch covers filter taps [tap0, tap0 + ntaps) of the kh*kw (a K-split partial convolution; default all)
     int pad_w, pad_h, stride_w, stride_h;   // A-load coordinate = tile origin * stride + tap - pad, per axis
     int tiles_w, tiles_h, tiles_n;
     int m_pairs, n_tiles;  // work items = m_pairs * n_tiles; a CTA pair handles M-tiles (2*mp, 2*mp+1) of one N-tile
@@ -94,14 +98,19 @@ struct ConvCfg {
     static constexpr int TMEM_COLS = (NBUF * TILE_COLS > 256) ? 512 : (NBUF * TILE_COLS > 128 ? 256 : 128);
     static constexpr int NUM_BARS = 3 * STAGES + 2 * NBUF + 2;
     static constexpr int SMEM_BYTES = PIPE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int THREADS = 448;
+    // converter warps: the fp16 split of a 16 KB tile costs ~2x the tf32 residual and, for tiles up to 128 wide, more than the
+    // MMAs of a k-block -> 8 warps there (two 16-byte pieces per thread), 4 otherwise
+    static constexpr int CONV_WARPS = (KIND == KIND_F16X3 && BLOCK_N <= 128) ? DT_CONV_WARPS_NARROW : 4;
+    static constexpr int CONV_THREADS = CONV_WARPS * 32;
+    static constexpr int EPI_WARP0 = 2 + CONV_WARPS;                 // first epilogue warp
+    static constexpr int THREADS = 64 + CONV_THREADS + 256;
     static_assert(TILE_COLS <= 512, "accumulators of one tile must fit TMEM");
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory limit");
     static_assert(8 * (NUM_BARS + 1) <= 256, "barrier area");
 };
 
 template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NMAIN, kTwoSM, KIND>::THREADS), 1) conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
     using Cfg = ConvCfg<BLOCK_N, NMAIN, kTwoSM, KIND>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int NBUF = Cfg::NBUF;
@@ -124,7 +133,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_kb = p.kh * p.kw * p.cin_blocks;
+    const int num_kb = p.ntaps * p.cin_blocks;
     const int num_items = p.m_pairs * p.n_tiles;
     const int pair = blockIdx.x >> 1;
     const int num_pairs = gridDim.x >> 1;
@@ -137,7 +146,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
         if (p.res_mode == RES_TILE) tma_prefetch_desc(&p.tm_r);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full(s), 1);
-            mbar_init(bar_conv(s), kTwoSM ? 256 : 128);     // 2-SM: the leader's issuer also waits for the peer's converters
+            mbar_init(bar_conv(s), (kTwoSM ? 2 : 1) * Cfg::CONV_THREADS);     // 2-SM: the leader's issuer also waits for the peer's converters
             mbar_init(bar_empty(s), kTwoSM ? 1 : 2);        // 1-SM: own MMA commit + the peer's (its multicast writes land in our stage too)
         }
         for (int b = 0; b < NBUF; ++b) {
@@ -179,8 +188,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(bar_empty(s), ph ^ 1u);
-                    const int tap = kb / p.cin_blocks;
-                    const int cb = kb - tap * p.cin_blocks;
+                    const int tap_l = kb / p.cin_blocks;
+                    const int cb = kb - tap_l * p.cin_blocks;
+                    const int tap = p.tap0 + tap_l;
+                    const int kbg = tap * p.cin_blocks + cb;        // k-block index into the full weight row
                     const int fy = tap / p.kw, fx = tap - fy * p.kw;
                     const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
                     mbar_arrive_expect_tx(bar_full(s), tx_bytes);
@@ -189,14 +200,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
                     const int nrow = n0 + (int)cta_rank * (BLOCK_N / 2);
                     if constexpr (kTwoSM) {
                         // 2-SM MMA: the half stays local (the pair's tensor cores read both halves in place)
-                        tma_load_2d(st + 2 * Cfg::A_BYTES, &p.tm_bhi, bar_full(s), kb * 32, nrow);
-                        if (p.passes == 3) tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &p.tm_blo, bar_full(s), kb * 32, nrow);
+                        tma_load_2d(st + 2 * Cfg::A_BYTES, &p.tm_bhi, bar_full(s), kbg * 32, nrow);
+                        if (p.passes == 3) tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &p.tm_blo, bar_full(s), kbg * 32, nrow);
                     } else {
                         // 1-SM MMA: multicast to both CTAs of the pair
                         const uint32_t half = cta_rank * (Cfg::B_BYTES / 2);
-                        tma_load_2d_mcast(st + 2 * Cfg::A_BYTES + half, &p.tm_bhi, bar_full(s), kb * 32, nrow, (uint16_t)3);
+                        tma_load_2d_mcast(st + 2 * Cfg::A_BYTES + half, &p.tm_bhi, bar_full(s), kbg * 32, nrow, (uint16_t)3);
                         if (p.passes == 3)
-                            tma_load_2d_mcast(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + half, &p.tm_blo, bar_full(s), kb * 32, nrow, (uint16_t)3);
+                            tma_load_2d_mcast(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + half, &p.tm_blo, bar_full(s), kbg * 32, nrow, (uint16_t)3);
                     }
                 }
             }
@@ -271,9 +282,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
                 __syncwarp();
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < Cfg::EPI_WARP0) {
         // ================================================================ A_lo converters (128 threads)
-        const int ct = threadIdx.x - 64;    // 0..127
+        const int ct = threadIdx.x - 64;    // 0..CONV_THREADS-1
         uint32_t it = 0;
         for (int item = pair; item < num_items; item += num_pairs) {
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
@@ -289,10 +300,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
                     bool bad = false;
                     // rows past the TMA box (boxes smaller than 128 pixels) are never written: whatever they hold produces accumulator
                     // rows that are never stored, but it must not trip the range flag
-                    const bool live_row = ct * 128 < p.a_tile_bytes;
+                    const bool live_row = (ct & 127) * 128 < p.a_tile_bytes;
+                    constexpr int PIECES = 4 * 128 / Cfg::CONV_THREADS;        // 16-byte fp16 pieces per thread (4 or 2)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = ct, c8 = i;
+                    for (int i = 0; i < PIECES; ++i) {
+                        const int r = ct & 127, c8 = (ct >> 7) * PIECES + i;
                         const float4 v0 = *reinterpret_cast<const float4*>(a32 + r * 128 + (((2 * c8) ^ (r & 7)) << 4));
                         const float4 v1 = *reinterpret_cast<const float4*>(a32 + r * 128 + (((2 * c8 + 1) ^ (r & 7)) << 4));
                         const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -335,8 +347,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 1) conv_tcgen05
         // Group g drains the live 32-channel chunks c with c % 2 == g through its own 16 KB staging slot, so two chunks are in
         // flight per tile and every SM sub-partition has two epilogue warps to hide TMEM / shared / global latencies.
         constexpr int NCHUNK = BLOCK_N / 32;
-        const int g = (warp - 6) >> 2;
-        const int et = threadIdx.x - 192 - 128 * g;   // 0..127 within the group
+        const int g = (warp - Cfg::EPI_WARP0) >> 2;
+        const int et = threadIdx.x - (64 + Cfg::CONV_THREADS) - 128 * g;   // 0..127 within the group
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;          // accumulator row == pixel slot in the box
         const uint32_t slot = epi_base + g * Cfg::A_BYTES;
