@@ -48,6 +48,9 @@ namespace dt {
 
 enum ConvResidualMode { RES_NONE = 0, RES_TILE = 1, RES_UPSAMPLE2X = 2 };
 enum ConvKind { KIND_TF32X3 = 0, KIND_F16X3 = 1 };
+#ifndef DT_CONV_EPI_SLOTS
+#define DT_CONV_EPI_SLOTS 1
+#endif
 #ifndef DT_CONV_WARPS_NARROW
 #define DT_CONV_WARPS_NARROW 4
 #endif
@@ -90,13 +93,18 @@ struct ConvCfg {
     static constexpr int B_BYTES = (kTwoSM ? BLOCK_N / 2 : BLOCK_N) * B_ROW_BYTES;
     // tf32: A, A_lo, B_hi, B_lo.   f16: A (fp32 staging), A_h + A_l (8 KB each, in the second 16 KB), B_h, B_l
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int STAGES = (196608 / STAGE_BYTES) > 4 ? 4 : (196608 / STAGE_BYTES);
+    // epilogue staging: each of the two epilogue groups owns EPI_SLOTS 16 KB slots (128 rows x 32 channels).  Two slots per group let
+    // the residual tile of the next chunk (RES_TILE) arrive, and the previous chunk's store drain, while the current chunk is computed;
+    // they are taken whenever at least 3 pipeline stages still fit beside them.
+    static constexpr int EPI_SLOTS = ((196608 - 2 * A_BYTES) / STAGE_BYTES >= 3) ? DT_CONV_EPI_SLOTS : 1;
+    static constexpr int EPI_BYTES = 2 * EPI_SLOTS * A_BYTES;
+    static constexpr int STAGES_FIT = (196608 + 2 * A_BYTES - EPI_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_FIT > 4 ? 4 : STAGES_FIT;
     static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
-    static constexpr int EPI_BYTES = 2 * A_BYTES;                    // 2 x (128 rows x 32 channels) staging ring
     static constexpr int TILE_COLS = (NMAIN + 1) * BLOCK_N;          // TMEM columns of one tile's accumulators
     static constexpr int NBUF = (2 * TILE_COLS <= 512) ? 2 : 1;      // double-buffer the accumulators when they fit
     static constexpr int TMEM_COLS = (NBUF * TILE_COLS > 256) ? 512 : (NBUF * TILE_COLS > 128 ? 256 : 128);
-    static constexpr int NUM_BARS = 3 * STAGES + 2 * NBUF + 2;
+    static constexpr int NUM_BARS = 3 * STAGES + 2 * NBUF + 2 * EPI_SLOTS;
     static constexpr int SMEM_BYTES = PIPE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     // converter warps: the fp16 split of a 16 KB tile costs ~2x the tf32 residual and, for tiles up to 128 wide, more than the
     // MMAs of a k-block -> 8 warps there (two 16-byte pieces per thread), 4 otherwise
@@ -127,7 +135,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
     auto bar_empty = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };            // both CTAs' MMAs retired
     auto bar_tfull = [&](int b) { return bar_base + 8u * (3 * STAGES + b); };            // a tile's accumulators complete
     auto bar_tempty = [&](int b) { return bar_base + 8u * (3 * STAGES + NBUF + b); };    // ... drained by the epilogue
-    auto bar_res = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 * NBUF + b); };   // residual chunk landed in epilogue group b's slot
+    auto bar_res = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 * NBUF + b); };   // residual chunk landed in epilogue slot b (group * EPI_SLOTS + slot)
     const uint32_t tmem_slot = bar_base + 8u * Cfg::NUM_BARS;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(epi_gen + Cfg::EPI_BYTES + 8 * Cfg::NUM_BARS);
 
@@ -153,8 +161,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
             mbar_init(bar_tfull(b), 1);
             mbar_init(bar_tempty(b), kTwoSM ? 512 : 256);   // 2-SM: both CTAs' epilogues release the leader's issuer
         }
-        mbar_init(bar_res(0), 1);
-        mbar_init(bar_res(1), 1);
+        for (int b = 0; b < 2 * Cfg::EPI_SLOTS; ++b) mbar_init(bar_res(b), 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -351,17 +358,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
         const int et = threadIdx.x - (64 + Cfg::CONV_THREADS) - 128 * g;   // 0..127 within the group
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;          // accumulator row == pixel slot in the box
-        const uint32_t slot = epi_base + g * Cfg::A_BYTES;
-        uint8_t* slot_gen = epi_gen + g * Cfg::A_BYTES;
-        uint32_t gc = 0;                        // chunks this group has processed -> residual-barrier phase
+        constexpr int NS = Cfg::EPI_SLOTS;
+        uint32_t gc = 0;                        // chunks this group has processed -> slot parity and residual-barrier phase
+        auto nlive_of = [&](int item_) {
+            int nl = (p.cout - (item_ % p.n_tiles) * BLOCK_N + 31) / 32;       // chunks past the true Cout are neither computed nor stored
+            return nl < 0 ? 0 : (nl > NCHUNK ? NCHUNK : nl);
+        };
+        // the group's next chunk after (item_, c_): same tile, or the first live chunk of a later tile
+        auto next_chunk = [&](int& item_, int& c_) {
+            c_ += 2;
+            while (item_ < num_items && c_ >= nlive_of(item_)) { item_ += num_pairs; c_ = g; }
+            return item_ < num_items;
+        };
+        auto issue_residual = [&](int item_, int c_, uint32_t gcn) {     // et == 0 only: residual tile chunk -> slot of chunk number gcn
+            int w0_, h0_, n0img_, n0_;
+            tile_of(item_, w0_, h0_, n0img_, n0_);
+            const uint32_t sl = (uint32_t)(g * NS) + (gcn % NS);
+            mbar_arrive_expect_tx(bar_res(sl), (uint32_t)p.a_tile_bytes);
+            tma_load_4d(epi_base + sl * Cfg::A_BYTES, &p.tm_r, bar_res(sl), n0_ + c_ * 32, w0_, h0_, n0img_);
+        };
+        if (et == 0 && p.res_mode == RES_TILE) {       // residual of the group's very first chunk
+            int it0 = pair, c0 = g - 2;
+            if (next_chunk(it0, c0)) issue_residual(it0, c0, 0u);
+        }
         int t = 0;
         for (int item = pair; item < num_items; item += num_pairs, ++t) {
             int w0, h0, n0img, n0;
             tile_of(item, w0, h0, n0img, n0);
             const int buf = t % NBUF;
             const int nacc = (num_kb < NMAIN ? num_kb : NMAIN);
-            int nlive = (p.cout - n0 + 31) / 32;       // chunks past the true Cout are neither computed nor stored
-            nlive = nlive < 0 ? 0 : (nlive > NCHUNK ? NCHUNK : nlive);
+            const int nlive = nlive_of(item);
             // pixel coordinates of this row (needed for the upsample operand)
             int pw_ = 0, ph_ = 0, pn_ = 0;
             bool row_valid = false;
@@ -384,6 +410,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
 #pragma unroll 1
             for (int c = g; c < nlive; c += 2, ++gc) {
                 const int ch0 = n0 + c * 32;
+                const uint32_t sidx = (uint32_t)(g * NS) + (gc % NS);
+                const uint32_t slot = epi_base + sidx * Cfg::A_BYTES;
+                uint8_t* slot_gen = epi_gen + sidx * Cfg::A_BYTES;
                 // upsample operand of this chunk: requested from global BEFORE the TMEM reads (latency overlap)
                 float4 rr[8];
                 {
@@ -396,15 +425,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                     for (int j = 0; j < 8; ++j)
                         rr[j] = (rp != nullptr && ch0 + j * 4 < p.cout) ? __ldg(reinterpret_cast<const float4*>(rp) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                // the group's previous TMA store must have finished READING the slot; then the residual tile chunk (RES_TILE)
-                // is landed in the slot by TMA (hardware clipping / zero fill handles the tile edges)
-                if (et == 0) {
-                    tma_store_wait_read0();
-                    if (p.res_mode == RES_TILE) {
-                        mbar_arrive_expect_tx(bar_res(g), (uint32_t)p.a_tile_bytes);
-                        tma_load_4d(slot, &p.tm_r, bar_res(g), ch0, w0, h0, n0img);
-                    }
-                }
+                // thread 0 of the group has, at the end of the previous chunk, waited until the store that last used this slot finished
+                // reading it and (RES_TILE) started the TMA load of this chunk's residual tile into it
                 named_bar_sync(1 + g, 128);
                 uint32_t v[32];
                 const uint32_t tbase = tbase0 + (uint32_t)(c * 32);
@@ -425,7 +447,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                     tc_fence_before();
                     if constexpr (kTwoSM) mbar_arrive_cluster(mapa_cluster(bar_tempty(buf), 0)); else mbar_arrive(bar_tempty(buf));
                 }
-                if (p.res_mode == RES_TILE) mbar_wait(bar_res(g), gc & 1u);
+                if (p.res_mode == RES_TILE) mbar_wait(bar_res(sidx), (gc / NS) & 1u);
                 float* stg = reinterpret_cast<float*>(slot_gen + row * 128);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {       // 8 x 16-byte pieces of this row's 128-byte line
@@ -465,6 +487,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                 if (et == 0) {
                     tma_store_4d(&p.tm_d, slot, ch0, w0, h0, n0img);
                     tma_store_commit();
+                    // free the slot the NEXT chunk will use (its last store must have finished reading shared memory) and start that
+                    // chunk's residual load, so that both overlap the next chunk's TMEM reads
+                    int itn = item, cn = c;
+                    if (next_chunk(itn, cn)) {
+                        tma_store_wait_read<NS - 1>();
+                        if (p.res_mode == RES_TILE) issue_residual(itn, cn, gc + 1);
+                    }
                 }
             }
         }

@@ -33,7 +33,7 @@ def acc():
         print("ACC N%d %dx%d Cin%d Cout%d k%d  tf32 %.2e  f16 %.2e" % (N, H, W, Cin, Cout, k, out["tf32"], out["f16"]), flush=True)
 
 
-def timing(only=None):
+def timing(only=None, with_res=False):
     shapes = [("P2 3x3 256->256 200x304", 8, 200, 304, 256, 256, 3, 1, 1, 0), ("C4 3x3 256->256 50x76", 8, 50, 76, 256, 256, 3, 1, 1, 0),
               ("C4 1x1 1024->256", 8, 50, 76, 1024, 256, 1, 0, 1, 0), ("C4 1x1 256->1024", 8, 50, 76, 256, 1024, 1, 0, 1, 0),
               ("C2 3x3 64->64 200x304", 8, 200, 304, 64, 64, 3, 1, 1, 0), ("C2 1x1 64->256", 8, 200, 304, 64, 256, 1, 0, 1, 0),
@@ -52,17 +52,19 @@ def timing(only=None):
         sc16 = (one / mult).contiguous()
         Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
         out = torch.empty((N, Ho, Wo, Cout), device=dev)
+        res = torch.randn((N, Ho, Wo, Cout), device=dev) if with_res else None
+        rp, rm = (ops._p(res), 1) if with_res else (None, 0)
         L = ops._lib.lib()
         fl = 2.0 * N * Ho * Wo * Cout * Cin * k * k
-        res = {}
+        tms = {}
         for kind in ("tf32", "f16"):
             def run():
                 if kind == "tf32":
-                    L.dt_conv2d_nhwc(ops._p(x), N, H, W, Cin, Cin, ops._p(w), ops._p(wl), Cout, k, k, pad, stride, ops._p(one), ops._p(zero), None, 0,
+                    L.dt_conv2d_nhwc(ops._p(x), N, H, W, Cin, Cin, ops._p(w), ops._p(wl), Cout, k, k, pad, stride, ops._p(one), ops._p(zero), rp, rm,
                                      None, 0, 0, 1, 0, 3, fbn, ops._p(out), Cout, ops._stream())
                 else:
                     L.dt_conv2d_nhwc_f16x3(ops._p(x), N, H, W, Cin, Cin, ops._p(hi), ops._p(lo), Cout, k, k, pad, stride, ops._p(sc16), ops._p(zero),
-                                           None, 0, None, 0, 0, 1, 0, 3, fbn, None, ops._p(out), Cout, ops._stream())
+                                           rp, rm, None, 0, 0, 1, 0, 3, fbn, None, ops._p(out), Cout, ops._stream())
             for _ in range(2):
                 run()
             torch.cuda.synchronize()
@@ -73,9 +75,9 @@ def timing(only=None):
                 e0.record(); run(); e1.record()
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
-            res[kind] = sorted(ts)[2]
+            tms[kind] = sorted(ts)[2]
         print("TIME %-30s tf32 %8.1f us (%6.1f TF/s alg)   f16 %8.1f us (%6.1f TF/s alg)   x%.2f" %
-              (name, res["tf32"] * 1e3, fl / res["tf32"] / 1e9, res["f16"] * 1e3, fl / res["f16"] / 1e9, res["tf32"] / res["f16"]), flush=True)
+              (name, tms["tf32"] * 1e3, fl / tms["tf32"] / 1e9, tms["f16"] * 1e3, fl / tms["f16"] / 1e9, tms["tf32"] / tms["f16"]), flush=True)
 
 
 if __name__ == "__main__":
@@ -88,3 +90,5 @@ if __name__ == "__main__":
         timing(only=[1, 2])
     if "mask" in which:
         timing(only=[7])
+    if "res" in which:
+        timing(only=[3, 5], with_res=True)
