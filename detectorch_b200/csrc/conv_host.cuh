@@ -93,6 +93,7 @@ struct ConvLayer {
     int nmain = 1;      // rotating main-term accumulators (3 = precise: shorter truncating accumulation chains)
     bool two_sm = true; // cta_group::2 MMA (default) vs 1-SM MMA + multicast (DT_CONV_1SM=1)
     int kind = KIND_TF32X3;
+    int ring = 0;       // residual prefetch ring (short-K RES_TILE layers)
     dim3 grid;
     bool valid = false;
 };
@@ -232,6 +233,11 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
     // K <= 512 (where the epilogue is as long as the MMAs, and the accumulation chains are short) use one merged accumulator instead
     L->nmain = (bn == 64) ? 3 : ((bn == 128 && s.precise) ? 3 : ((bn == 256 && conv_merge_acc(p.ntaps * p.cin_blocks)) ? 0 : 1));
     finish_grid(L, ceil_div(s.Cout, bn));
+    {
+        static int use_ring = -1;
+        if (use_ring < 0) { const char* e = getenv("DT_CONV_RES_RING"); use_ring = e ? atoi(e) : 1; }
+        L->ring = (use_ring && L->nmain == 0 && L->two_sm && L->kind == KIND_F16X3 && s.res_mode == RES_TILE) ? 1 : 0;
+    }
     return true;
 }
 
@@ -274,25 +280,32 @@ inline bool conv_build_stem(const float* x4, int B, int Hp, int Wp, int H1, int 
     return true;
 }
 
-template <int BN, int NM, bool TWO, int KIND>
+template <int BN, int NM, bool TWO, int KIND, int RING = 0>
 inline cudaError_t conv_launch_cfg(const ConvLayer& L, cudaStream_t stream) {
-    using Cfg = ConvCfg<BN, NM, TWO, KIND>;
+    using Cfg = ConvCfg<BN, NM, TWO, KIND, RING>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel<BN, NM, TWO, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel<BN, NM, TWO, KIND, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    conv_tcgen05_kernel<BN, NM, TWO, KIND><<<L.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(L.p);
+    conv_tcgen05_kernel<BN, NM, TWO, KIND, RING><<<L.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(L.p);
     return cudaGetLastError();
 }
+
+constexpr int kConvResRing = 3;
 
 template <bool TWO, int KIND>
 inline cudaError_t conv_launch_sm(const ConvLayer& L, cudaStream_t stream) {
     switch (L.block_n) {
         case 64: return conv_launch_cfg<64, 3, TWO, KIND>(L, stream);
         case 128: return L.nmain == 3 ? conv_launch_cfg<128, 3, TWO, KIND>(L, stream) : conv_launch_cfg<128, 1, TWO, KIND>(L, stream);
-        case 256: return L.nmain == 0 ? conv_launch_cfg<256, 0, TWO, KIND>(L, stream) : conv_launch_cfg<256, 1, TWO, KIND>(L, stream);
+        case 256:
+            if (L.nmain == 0) {
+                if constexpr (TWO && KIND == KIND_F16X3) { if (L.ring) return conv_launch_cfg<256, 0, TWO, KIND, kConvResRing>(L, stream); }
+                return conv_launch_cfg<256, 0, TWO, KIND>(L, stream);
+            }
+            return conv_launch_cfg<256, 1, TWO, KIND>(L, stream);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -82,7 +82,7 @@ struct ConvParams {
     int* range_flag;       // KIND_F16X3: set to 1 when an activation does not fit fp16 (|x| >= 65504 or NaN); may be null
 };
 
-template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND>
+template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND, int RING = 0>
 struct ConvCfg {
     static constexpr int BLOCK_M = 128;
     static constexpr int BLOCK_K = 32;
@@ -96,16 +96,21 @@ struct ConvCfg {
     // epilogue staging: each of the two epilogue groups owns EPI_SLOTS 16 KB slots (128 rows x 32 channels).  Two slots per group let
     // the residual tile of the next chunk (RES_TILE) arrive, and the previous chunk's store drain, while the current chunk is computed;
     // they are taken whenever at least 3 pipeline stages still fit beside them.
-    static constexpr int EPI_SLOTS = ((196608 - 2 * A_BYTES) / STAGE_BYTES >= 3) ? DT_CONV_EPI_SLOTS : 1;
+    static constexpr int EPI_SLOTS = (RING == 0 && (196608 - 2 * A_BYTES) / STAGE_BYTES >= 3) ? DT_CONV_EPI_SLOTS : 1;
+    // RING > 0 (short-K residual layers, where the epilogue IS the kernel): a ring of RING residual tiles per epilogue group is
+    // prefetched by TMA RING chunks ahead, so the HBM latency of the residual never sits in the per-chunk chain; the mainloop
+    // (<= 16 k-blocks per tile) makes do with two pipeline stages.
+    static constexpr int RING_BYTES = 2 * RING * A_BYTES;
     static constexpr int EPI_BYTES = 2 * EPI_SLOTS * A_BYTES;
-    static constexpr int STAGES_FIT = (196608 + 2 * A_BYTES - EPI_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES_FIT = (196608 + 2 * A_BYTES - EPI_BYTES - RING_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_FIT > 4 ? 4 : STAGES_FIT;
     static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+    static_assert(STAGES >= 2, "pipeline too shallow");
     static constexpr int TILE_COLS = (NMAIN + 1) * BLOCK_N;          // TMEM columns of one tile's accumulators
     static constexpr int NBUF = (2 * TILE_COLS <= 512) ? 2 : 1;      // double-buffer the accumulators when they fit
     static constexpr int TMEM_COLS = (NBUF * TILE_COLS > 256) ? 512 : (NBUF * TILE_COLS > 128 ? 256 : 128);
-    static constexpr int NUM_BARS = 3 * STAGES + 2 * NBUF + 2 * EPI_SLOTS;
-    static constexpr int SMEM_BYTES = PIPE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int NUM_BARS = 3 * STAGES + 2 * NBUF + 2 * EPI_SLOTS + 2 * RING;
+    static constexpr int SMEM_BYTES = PIPE_BYTES + EPI_BYTES + RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     // converter warps: the fp16 split of a 16 KB tile costs ~2x the tf32 residual and, for tiles up to 128 wide, more than the
     // MMAs of a k-block -> 8 warps there (two 16-byte pieces per thread), 4 otherwise
     static constexpr int CONV_WARPS = (KIND == KIND_F16X3 && BLOCK_N <= 128) ? DT_CONV_WARPS_NARROW : 4;
@@ -117,9 +122,9 @@ struct ConvCfg {
     static_assert(8 * (NUM_BARS + 1) <= 256, "barrier area");
 };
 
-template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NMAIN, kTwoSM, KIND>::THREADS), 1) conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
-    using Cfg = ConvCfg<BLOCK_N, NMAIN, kTwoSM, KIND>;
+template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND, int RING = 0>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NMAIN, kTwoSM, KIND, RING>::THREADS), 1) conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
+    using Cfg = ConvCfg<BLOCK_N, NMAIN, kTwoSM, KIND, RING>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int NBUF = Cfg::NBUF;
     extern __shared__ uint8_t smem_raw[];
@@ -128,7 +133,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t epi_base = smem_base + Cfg::PIPE_BYTES;
     uint8_t* epi_gen = smem_gen + Cfg::PIPE_BYTES;
-    const uint32_t bar_base = epi_base + Cfg::EPI_BYTES;
+    const uint32_t ring_base = epi_base + Cfg::EPI_BYTES;          // residual prefetch ring (RING > 0)
+    uint8_t* ring_gen = epi_gen + Cfg::EPI_BYTES;
+    const uint32_t bar_base = ring_base + Cfg::RING_BYTES;
     // barrier slots (8 B each)
     auto bar_full = [&](int s) { return bar_base + 8u * s; };                            // TMA bytes landed
     auto bar_conv = [&](int s) { return bar_base + 8u * (STAGES + s); };                 // A_lo published
@@ -136,8 +143,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
     auto bar_tfull = [&](int b) { return bar_base + 8u * (3 * STAGES + b); };            // a tile's accumulators complete
     auto bar_tempty = [&](int b) { return bar_base + 8u * (3 * STAGES + NBUF + b); };    // ... drained by the epilogue
     auto bar_res = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 * NBUF + b); };   // residual chunk landed in epilogue slot b (group * EPI_SLOTS + slot)
+    auto bar_ring = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 * NBUF + 2 * Cfg::EPI_SLOTS + b); };   // ... in ring slot b (group * RING + r)
     const uint32_t tmem_slot = bar_base + 8u * Cfg::NUM_BARS;
-    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(epi_gen + Cfg::EPI_BYTES + 8 * Cfg::NUM_BARS);
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(epi_gen + Cfg::EPI_BYTES + Cfg::RING_BYTES + 8 * Cfg::NUM_BARS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -162,6 +170,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
             mbar_init(bar_tempty(b), kTwoSM ? 512 : 256);   // 2-SM: both CTAs' epilogues release the leader's issuer
         }
         for (int b = 0; b < 2 * Cfg::EPI_SLOTS; ++b) mbar_init(bar_res(b), 1);
+        for (int b = 0; b < 2 * RING; ++b) mbar_init(bar_ring(b), 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -377,9 +386,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
             mbar_arrive_expect_tx(bar_res(sl), (uint32_t)p.a_tile_bytes);
             tma_load_4d(epi_base + sl * Cfg::A_BYTES, &p.tm_r, bar_res(sl), n0_ + c_ * 32, w0_, h0_, n0img_);
         };
-        if (et == 0 && p.res_mode == RES_TILE) {       // residual of the group's very first chunk
-            int it0 = pair, c0 = g - 2;
-            if (next_chunk(it0, c0)) issue_residual(it0, c0, 0u);
+        // RING > 0: a separate prefetch stream runs RING chunks ahead of the consumer
+        int pf_item = pair, pf_c = g - 2;
+        uint32_t pf_n = 0;                      // chunks whose residual load has been issued
+        auto issue_ring = [&]() {               // et == 0 only
+            if (!next_chunk(pf_item, pf_c)) return;
+            int w0_, h0_, n0img_, n0_;
+            tile_of(pf_item, w0_, h0_, n0img_, n0_);
+            const uint32_t sl = (uint32_t)(g * RING) + (pf_n % (RING > 0 ? RING : 1));
+            mbar_arrive_expect_tx(bar_ring(sl), (uint32_t)p.a_tile_bytes);
+            tma_load_4d(ring_base + sl * Cfg::A_BYTES, &p.tm_r, bar_ring(sl), n0_ + pf_c * 32, w0_, h0_, n0img_);
+            ++pf_n;
+        };
+        if (et == 0 && p.res_mode == RES_TILE) {
+            if constexpr (RING > 0) {
+                for (int r = 0; r < RING; ++r) issue_ring();
+            } else {                                   // residual of the group's very first chunk
+                int it0 = pair, c0 = g - 2;
+                if (next_chunk(it0, c0)) issue_residual(it0, c0, 0u);
+            }
         }
         int t = 0;
         for (int item = pair; item < num_items; item += num_pairs, ++t) {
@@ -447,7 +472,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                     tc_fence_before();
                     if constexpr (kTwoSM) mbar_arrive_cluster(mapa_cluster(bar_tempty(buf), 0)); else mbar_arrive(bar_tempty(buf));
                 }
-                if (p.res_mode == RES_TILE) mbar_wait(bar_res(sidx), (gc / NS) & 1u);
+                const float4* rsrc = nullptr;           // this row's residual line (ring variant)
+                if (p.res_mode == RES_TILE) {
+                    if constexpr (RING > 0) {
+                        const uint32_t rs = (uint32_t)(g * RING) + (gc % RING);
+                        mbar_wait(bar_ring(rs), (gc / RING) & 1u);
+                        rsrc = reinterpret_cast<const float4*>(ring_gen + rs * Cfg::A_BYTES + row * 128);
+                    } else {
+                        mbar_wait(bar_res(sidx), (gc / NS) & 1u);
+                    }
+                }
                 float* stg = reinterpret_cast<float*>(slot_gen + row * 128);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {       // 8 x 16-byte pieces of this row's 128-byte line
@@ -465,7 +499,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                     const int pj = j ^ (row & 7);      // SWIZZLE_128B: 16-byte piece index XOR (row mod 8)
                     float4* sl = reinterpret_cast<float4*>(stg) + pj;
                     if (p.res_mode == RES_TILE) {
-                        const float4 r = *sl;
+                        const float4 r = (RING > 0) ? rsrc[pj] : *sl;
                         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
                     } else {
                         o.x += rr[j].x; o.y += rr[j].y; o.z += rr[j].z; o.w += rr[j].w;       // zeros when there is no operand
@@ -490,7 +524,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                     // free the slot the NEXT chunk will use (its last store must have finished reading shared memory) and start that
                     // chunk's residual load, so that both overlap the next chunk's TMEM reads
                     int itn = item, cn = c;
-                    if (next_chunk(itn, cn)) {
+                    if constexpr (RING > 0) {
+                        // every thread of the group is past its reads of this chunk's ring slot (named barrier above): refill it
+                        if (p.res_mode == RES_TILE) issue_ring();
+                        if (next_chunk(itn, cn)) tma_store_wait_read<NS - 1>();
+                    } else if (next_chunk(itn, cn)) {
                         tma_store_wait_read<NS - 1>();
                         if (p.res_mode == RES_TILE) issue_residual(itn, cn, gc + 1);
                     }
