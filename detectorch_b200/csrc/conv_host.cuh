@@ -236,7 +236,9 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
     {
         static int use_ring = -1;
         if (use_ring < 0) { const char* e = getenv("DT_CONV_RES_RING"); use_ring = e ? atoi(e) : 1; }
-        L->ring = (use_ring && L->nmain == 0 && L->two_sm && L->kind == KIND_F16X3 && s.res_mode == RES_TILE) ? 1 : 0;
+        // measured: -15..26 % on the K <= 256 residual layers (conv3 of the 64/128/256-channel stages), +11 % on K = 512 (two pipeline
+        // stages are too few for 16 k-blocks per tile)
+        L->ring = (use_ring && L->nmain == 0 && L->two_sm && L->kind == KIND_F16X3 && s.res_mode == RES_TILE && p.ntaps * p.cin_blocks <= 8) ? 1 : 0;
     }
     return true;
 }
