@@ -100,7 +100,7 @@ def run_reference(args):
                                                            "+ greedy NMS), 1 image per step (bounded sample of the batch-8 workload)"},
             "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": n, "kind": "port", "sample": "%d x 1 image 3x800x1216" % steps},
             "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -264,12 +264,27 @@ def run_ours(args):
                         "ms_per_step": e2e_ms / steps, "note": "pinned host images -> H2D -> fused engine -> D2H boxes/scores/classes/counts/masks, 2-deep pipeline"},
                 "gpu_launches": launches_per_step * steps,
                 "roofline": roof, "roofline_roialign": roi_roof, "cpu_baseline": cpu_base}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_json_out = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else that libraries write to fd 1 (e.g. NCCL's version
+    banner on rank 0) was redirected to stderr in main()."""
+    out = _json_out if _json_out is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _json_out
+    sys.stdout.flush()
+    _json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

@@ -224,9 +224,10 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
 }
 // Instruction descriptor for kind::tf32 / kind::f16 with fp32 accumulate, K-major A and B
 //   [4,6) c_format=1(F32) | [7,10) a_format | [10,13) b_format | [17,23) N>>3 | [24,29) M>>4
-__host__ __device__ constexpr uint32_t umma_idesc(int fmt /*0=f16,1=bf16,2=tf32*/, int M, int N) {
-    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc2(int afmt, int bfmt /*0=f16,1=bf16,2=tf32*/, int M, int N) {
+    return (1u << 4) | ((uint32_t)afmt << 7) | ((uint32_t)bfmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) { return umma_idesc2(fmt, fmt, M, N); }
 
 // 32 lanes x 32 columns of fp32 accumulator: thread i of the warp gets row (lane base + i), columns [col, col+32)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {

@@ -48,6 +48,12 @@ namespace dt {
 
 enum ConvResidualMode { RES_NONE = 0, RES_TILE = 1, RES_UPSAMPLE2X = 2 };
 enum ConvKind { KIND_TF32X3 = 0, KIND_F16X3 = 1 };
+// Experiment switch (default off): store the low half of A as bf16 (a byte permute instead of a second fp32->fp16 conversion, which
+// would halve the load on the XU pipe that bounds the converter warps) and run the A_l * B_h term with A = bf16, B = fp16.  The
+// hardware rejects mixed A/B formats inside kind::f16 (illegal instruction on sm_100a), so both halves stay fp16.
+#ifndef DT_CONV_LO_BF16
+#define DT_CONV_LO_BF16 0
+#endif
 #ifndef DT_CONV_EPI_SLOTS
 #define DT_CONV_EPI_SLOTS 1
 #endif
@@ -230,10 +236,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
         }
     } else if (warp == 1) {
         // ================================================================ MMA issuer (one elected lane; 2-SM: leader CTA only)
-        constexpr uint32_t idesc = umma_idesc(KIND == KIND_F16X3 ? 0 : 2, kTwoSM ? 256 : 128, BLOCK_N);
+        constexpr uint32_t idesc_main = umma_idesc(KIND == KIND_F16X3 ? 0 : 2, kTwoSM ? 256 : 128, BLOCK_N);
         // one K step of the instruction = 32 bytes of a row: 8 tf32 or 16 fp16 elements -> 4 or 2 steps per 32-element k-block
         constexpr int KSTEPS = KIND == KIND_F16X3 ? 2 : 4;
-        auto mma = [&](uint32_t acc, uint64_t da_, uint64_t db_, uint32_t flag) {
+        constexpr uint32_t idesc_al = (KIND == KIND_F16X3 && DT_CONV_LO_BF16) ? umma_idesc2(1, 0, kTwoSM ? 256 : 128, BLOCK_N) : idesc_main;
+        auto mma = [&](uint32_t acc, uint64_t da_, uint64_t db_, uint32_t flag, uint32_t idesc_ = 0xffffffffu) {
+            const uint32_t idesc = idesc_ == 0xffffffffu ? idesc_main : idesc_;
             if constexpr (KIND == KIND_F16X3) {
                 if constexpr (kTwoSM) umma_f16_2sm(acc, da_, db_, idesc, flag); else umma_f16(acc, da_, db_, idesc, flag);
             } else {
@@ -282,7 +290,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                         const uint32_t main_flag = NMAIN == 0 ? ((p.passes == 3 || (kb | k) != 0) ? 1u : 0u) : ((kb >= NMAIN || k != 0) ? 1u : 0u);
                         if (p.passes == 3) {
                             const uint32_t acc_x = acc0 + (uint32_t)(NMAIN * BLOCK_N);
-                            mma(acc_x, dal + koff, dbh + koff, (kb | k) != 0);
+                            mma(acc_x, dal + koff, dbh + koff, (kb | k) != 0, idesc_al);
                             mma(acc_x, da + koff, dbl + koff, 1u);
                         }
                         mma(acc_main, da + koff, dbh + koff, main_flag);
@@ -330,7 +338,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                             const __half h0 = __float2half_rn(f[2 * j]), h1 = __float2half_rn(f[2 * j + 1]);
                             bad = bad || !(fabsf(f[2 * j]) < 65504.f) || !(fabsf(f[2 * j + 1]) < 65504.f);
                             hh[j] = __halves2half2(h0, h1);
+#if DT_CONV_LO_BF16
+                            {
+                                const uint32_t l0 = __float_as_uint(f[2 * j] - __half2float(h0)), l1 = __float_as_uint(f[2 * j + 1] - __half2float(h1));
+                                const uint32_t packed = __byte_perm(l0, l1, 0x7632);      // (l1.hi16 << 16) | l0.hi16: two truncated bf16
+                                ll[j] = *reinterpret_cast<const __half2*>(&packed);
+                            }
+#else
                             ll[j] = __halves2half2(__float2half_rn(f[2 * j] - __half2float(h0)), __float2half_rn(f[2 * j + 1] - __half2float(h1)));
+#endif
                         }
                         const int off = r * 64 + ((c8 ^ ((r >> 1) & 3)) << 4);
                         *reinterpret_cast<uint4*>(ah + off) = *reinterpret_cast<const uint4*>(hh);

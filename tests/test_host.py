@@ -15,14 +15,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def header_functions():
     src = open(os.path.join(ROOT, "include", "detectorch_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(dt_[a-z0-9_]+|launch_roi_align_forward_cuda)\s*\(", src)) - {"dt_engine_config"})
+    return sorted(set(re.findall(r"\b(dt_[a-z0-9_]+|launch_roi_align_[a-z]+_cuda)\s*\(", src)) - {"dt_engine_config"})
 
 
 def test_library_exports_every_declared_symbol(built):
     from detectorch_b200 import _lib
     L = ctypes.CDLL(_lib.LIB_PATH)
     names = header_functions()
-    assert "launch_roi_align_forward_cuda" in names and "dt_engine_run" in names and len(names) >= 18
+    assert "launch_roi_align_forward_cuda" in names and "launch_roi_align_backward_cuda" in names and "dt_engine_run" in names
+    assert "dt_segm_rle" in names and "dt_prep_image" in names and "dt_conv2d_nhwc_f16x3" in names and len(names) >= 33
     for n in names:
         assert hasattr(L, n), "library does not export %s" % n
     assert b"sm_100a" in _lib.lib().dt_version()
@@ -30,7 +31,8 @@ def test_library_exports_every_declared_symbol(built):
 
 def test_ctypes_signatures_cover_operator_api(built):
     from detectorch_b200 import _lib
-    for n in ("launch_roi_align_forward_cuda", "dt_roi_align_forward_nchw", "dt_roi_align_forward_nhwc", "dt_nms", "dt_conv2d_nhwc"):
+    for n in ("launch_roi_align_forward_cuda", "launch_roi_align_backward_cuda", "dt_roi_align_forward_nchw", "dt_roi_align_forward_nhwc", "dt_nms",
+              "dt_conv2d_nhwc", "dt_conv2d_nhwc_f16x3", "dt_fp16_split", "dt_segm_rle", "dt_segm_paste", "dt_prep_image"):
         assert n in _lib.SIGNATURES
 
 
