@@ -435,7 +435,7 @@ struct ProgBuilder {
     void conv(int stage, const std::string& wname, const float* x, int N, int H, int W, int xstride, float* y, int ystride, int kpad,
               int stride, bool relu, int res_mode = RES_NONE, const float* res = nullptr, const float* up = nullptr, int up_h = 0,
               int up_w = 0, int sigmoid_ch = 0, size_t w_extra_off = 0, int out_h = 0, int out_w = 0, int out_step = 0, int oy = 0,
-              int ox = 0, int force_bn = 0, int tap0 = 0, int ntaps = 0, bool zero_shift = false) {
+              int ox = 0, int force_bn = 0, int tap0 = 0, int ntaps = 0, bool zero_shift = false, int planes_in = 0, int planes_out = 0) {
         const ConvW& c = (*cw)[wname];
         ConvSpec s;
         memset(&s, 0, sizeof(s));
@@ -465,6 +465,12 @@ struct ProgBuilder {
             s.scale = e->wvec(c.scale);
         }
         s.y = y; s.y_pix_stride = ystride;
+        // fp16 hi/lo plane hand-over (kind::f16 only): the fp32 buffer of N*H*W*C floats holds the two fp16 planes back to back
+        if (planes_in && e->cfg.conv_kind == 0) s.x_lo = reinterpret_cast<const __half*>(x) + (size_t)N * H * W * c.cin;
+        if (planes_out && e->cfg.conv_kind == 0) {
+            const int Ho_ = (H + 2 * kpad - c.k) / stride + 1, Wo_ = (W + 2 * kpad - c.k) / stride + 1;
+            s.y_lo = reinterpret_cast<__half*>(y) + (size_t)N * Ho_ * Wo_ * c.cout;
+        }
         s.out_h = out_h; s.out_w = out_w; s.out_step = out_step; s.out_y0 = oy; s.out_x0 = ox;
         s.residual = res; s.res_pix_stride = c.cout; s.up_src = up; s.up_h = up_h; s.up_w = up_w;
         s.res_mode = res_mode; s.relu = relu ? 1 : 0; s.sigmoid_ch = sigmoid_ch; s.passes = e->cfg.passes; s.force_block_n = force_bn; s.precise = (force_bn == 128) ? 1 : 0;
@@ -624,8 +630,13 @@ bool build_program(Engine* e, std::map<std::string, ConvW>* cw) {
             const std::string wp = "model.layer" + std::to_string(li) + "." + std::to_string(b) + ".";
             const int stride = (b == 0 && li > 1) ? 2 : 1;
             const int ho = e->LH[li - 1], wo = e->LW[li - 1];
-            pb.conv(ST_TRUNK, wp + "conv1", x, B, h, w, cin, e->buf(p + ".t1"), planes, 0, stride, true);
-            pb.conv(ST_TRUNK, wp + "conv2", e->buf(p + ".t1"), B, ho, wo, planes, e->buf(p + ".t2"), planes, 1, 1, true);
+            // conv1 -> conv2 hand-over as fp16 hi/lo planes: the 3x3 conv would otherwise re-convert every input element once per filter tap
+            // (the converter warps' fp32->fp16 packs are what bounds the 64/128-wide layers)
+            const int pl = c.plane_handover ? 1 : 0;
+            pb.conv(ST_TRUNK, wp + "conv1", x, B, h, w, cin, e->buf(p + ".t1"), planes, 0, stride, true, RES_NONE, nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                    0, 0, 0, false, 0, pl);
+            pb.conv(ST_TRUNK, wp + "conv2", e->buf(p + ".t1"), B, ho, wo, planes, e->buf(p + ".t2"), planes, 1, 1, true, RES_NONE, nullptr, nullptr, 0, 0, 0,
+                    0, 0, 0, 0, 0, 0, 0, 0, 0, false, pl, 0);
             const float* idt = x;
             if (b == 0) {
                 pb.conv(ST_TRUNK, wp + "downsample.0", x, B, h, w, cin, e->buf(p + ".ds"), planes * 4, 0, stride, false);

@@ -86,6 +86,25 @@ inline bool make_tmap_2d_f16(CUtensorMap* tm, const void* base, uint64_t d0, uin
     return true;
 }
 
+// 4D fp16 plane map {C (contiguous), W, H, N}, box {32 channels = 64 bytes, ...}, SWIZZLE_64B (activations handed over as hi/lo planes)
+inline bool make_tmap_4d_f16(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint64_t s1, uint64_t s2,
+                             uint64_t s3, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3, uint32_t e1 = 1, uint32_t e2 = 1) {
+    auto fn = get_tmap_encode();
+    if (!fn) return false;
+    cuuint64_t dims[4] = {d0, d1, d2, d3};
+    cuuint64_t strides[3] = {s1, s2, s3};
+    cuuint32_t box[4] = {b0, b1, b2, b3};
+    cuuint32_t estr[4] = {1, e1, e2, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "[detectorch_b200] cuTensorMapEncodeTiled(4d f16) failed: %d dims=(%llu,%llu,%llu,%llu) box=(%u,%u,%u,%u)\n", (int)r,
+                (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)d3, b0, b1, b2, b3);
+        return false;
+    }
+    return true;
+}
+
 // A conv layer instance: everything needed to (re)launch it.  Built once per (layer, shape).
 struct ConvLayer {
     ConvParams p;
@@ -114,6 +133,9 @@ struct ConvSpec {
     const float* residual; int res_pix_stride;    // RES_TILE: same geometry as the (plain) output
     const float* up_src; int up_h, up_w;          // RES_UPSAMPLE2X
     int res_mode, relu, sigmoid_ch, passes;
+    // fp16 hi/lo plane hand-over between two KIND_F16X3 layers (dense channel stride only): x / y then point at the HIGH plane and
+    // x_lo / y_lo at the LOW plane, each [N,H,W,C] fp16
+    const void* x_lo; void* y_lo;
     int tap0, ntaps;                              // K-split: only filter taps [tap0, tap0+ntaps) (ntaps == 0: all kh*kw)
     int force_block_n;                            // 0 = auto
     int precise;                                  // BLOCK_N == 128 only: 3 rotating accumulators instead of TMEM double-buffering
@@ -189,8 +211,15 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
     L->block_n = bn;
     const int K = s.kh * s.kw * s.Cin;
     const uint64_t xs = (uint64_t)s.x_pix_stride * 4;
-    if (!make_tmap_4d(&p.tm_a, s.x, s.Cin, s.W, s.H, s.N, xs, xs * s.W, xs * s.W * s.H, 32, wbox * s.stride, hbox * s.stride, nbox,
-                      s.stride, s.stride))
+    if (s.x_lo) {
+        if (s.kind != KIND_F16X3 || s.x_pix_stride != s.Cin) { fprintf(stderr, "[detectorch_b200] conv_build: fp16 input planes need the f16 kind and a dense layout\n"); return false; }
+        const uint64_t hs = (uint64_t)s.Cin * 2;
+        if (!make_tmap_4d_f16(&p.tm_a, s.x, s.Cin, s.W, s.H, s.N, hs, hs * s.W, hs * s.W * s.H, 32, wbox * s.stride, hbox * s.stride, nbox, s.stride, s.stride) ||
+            !make_tmap_4d_f16(&p.tm_a2, s.x_lo, s.Cin, s.W, s.H, s.N, hs, hs * s.W, hs * s.W * s.H, 32, wbox * s.stride, hbox * s.stride, nbox, s.stride, s.stride))
+            return false;
+        p.a_planes = 1;
+    } else if (!make_tmap_4d(&p.tm_a, s.x, s.Cin, s.W, s.H, s.N, xs, xs * s.W, xs * s.W * s.H, 32, wbox * s.stride, hbox * s.stride, nbox,
+                             s.stride, s.stride))
         return false;
     // each CTA of a pair fetches half of the BLOCK_N weight rows and multicasts them
     if (s.kind == KIND_F16X3) {
@@ -203,7 +232,17 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
     L->kind = s.kind == KIND_F16X3 ? KIND_F16X3 : KIND_TF32X3;
     p.range_flag = s.range_flag;
     const uint64_t ys = (uint64_t)s.y_pix_stride * 4;
-    if (s.out_step == 0) {
+    if (s.y_lo) {
+        if (s.kind != KIND_F16X3 || s.out_step != 0 || s.y_pix_stride != s.Cout || s.res_mode != RES_NONE || (s.Cout % 32) != 0) {
+            fprintf(stderr, "[detectorch_b200] conv_build: fp16 output planes need the f16 kind, a dense layout, Cout %% 32 == 0 and no residual\n");
+            return false;
+        }
+        const uint64_t hs = (uint64_t)s.Cout * 2;
+        if (!make_tmap_4d_f16(&p.tm_d, s.y, s.Cout, Wo, Ho, s.N, hs, hs * Wo, hs * Wo * Ho, 32, wbox, hbox, nbox) ||
+            !make_tmap_4d_f16(&p.tm_d2, s.y_lo, s.Cout, Wo, Ho, s.N, hs, hs * Wo, hs * Wo * Ho, 32, wbox, hbox, nbox))
+            return false;
+        p.out_planes = 1;
+    } else if (s.out_step == 0) {
         if (!make_tmap_4d(&p.tm_d, s.y, s.Cout, Wo, Ho, s.N, ys, ys * Wo, ys * Wo * Ho, 32, wbox, hbox, nbox)) return false;
     } else {
         // strided scatter view: logical (w,h) -> physical (w*step + x0, h*step + y0) of an [N,out_h,out_w] map

@@ -67,6 +67,8 @@ struct ConvParams {
     CUtensorMap tm_blo;    // 2D {K, Cout} B - trunc_tf32(B)
     CUtensorMap tm_d;      // 4D {Cout, Wo, Ho, N} over the NHWC output, box {32, wbox, hbox, nbox}
     CUtensorMap tm_r;      // 4D residual, same geometry as tm_d (RES_TILE only)
+    CUtensorMap tm_a2;     // a_planes: the fp16 LOW plane of the input (tm_a is then the fp16 HIGH plane), SWIZZLE_64B boxes of 32 channels
+    CUtensorMap tm_d2;     // out_planes: the fp16 LOW plane of the output (tm_d the HIGH plane), SWIZZLE_64B boxes of 32 channels
     const float* scale;    // [Cout] per-channel scale (folded BN gain, or 1)
     const float* shift;    // [Cout] per-channel shift (folded BN bias, or conv bias)
     const float* up_src;   // RES_UPSAMPLE2X: coarser NHWC map [N, up_h, up_w, Cout]
@@ -85,6 +87,9 @@ struct ConvParams {
     int sigmoid_ch;        // channels [0, sigmoid_ch) get a sigmoid (RPN objectness), after bias
     int res_mode;
     int passes;            // 3 = error-compensated three-term product (default), 1 = single pass
+    int a_planes;          // KIND_F16X3: the input already is a pair of fp16 planes (hi, lo) written by the producing layer: the A_h / A_l
+                           // operand tiles arrive by TMA and the converter warps have nothing to do
+    int out_planes;        // KIND_F16X3: write the output as a pair of fp16 planes (hi = fp16(y), lo = fp16(y - hi)) instead of fp32
     int* range_flag;       // KIND_F16X3: set to 1 when an activation does not fit fp16 (|x| >= 65504 or NaN); may be null
 };
 
@@ -166,6 +171,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
         tma_prefetch_desc(&p.tm_blo);
         tma_prefetch_desc(&p.tm_d);
         if (p.res_mode == RES_TILE) tma_prefetch_desc(&p.tm_r);
+        if (p.a_planes) tma_prefetch_desc(&p.tm_a2);
+        if (p.out_planes) tma_prefetch_desc(&p.tm_d2);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full(s), 1);
             mbar_init(bar_conv(s), (kTwoSM ? 2 : 1) * Cfg::CONV_THREADS);     // 2-SM: the leader's issuer also waits for the peer's converters
@@ -217,7 +224,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                     const int fy = tap / p.kw, fx = tap - fy * p.kw;
                     const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
                     mbar_arrive_expect_tx(bar_full(s), tx_bytes);
-                    tma_load_4d(st, &p.tm_a, bar_full(s), cb * 32, w0 * p.stride_w + fx - p.pad_w, h0 * p.stride_h + fy - p.pad_h, n0img);
+                    if (KIND == KIND_F16X3 && p.a_planes) {
+                        // fp16 planes: the two operand tiles land where the converters would have written them
+                        tma_load_4d(st + Cfg::A_BYTES, &p.tm_a, bar_full(s), cb * 32, w0 * p.stride_w + fx - p.pad_w, h0 * p.stride_h + fy - p.pad_h, n0img);
+                        tma_load_4d(st + Cfg::A_BYTES + Cfg::A_BYTES / 2, &p.tm_a2, bar_full(s), cb * 32, w0 * p.stride_w + fx - p.pad_w,
+                                    h0 * p.stride_h + fy - p.pad_h, n0img);
+                    } else {
+                        tma_load_4d(st, &p.tm_a, bar_full(s), cb * 32, w0 * p.stride_w + fx - p.pad_w, h0 * p.stride_h + fy - p.pad_h, n0img);
+                    }
                     // this CTA's half of the weight rows
                     const int nrow = n0 + (int)cta_rank * (BLOCK_N / 2);
                     if constexpr (kTwoSM) {
@@ -315,7 +329,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
                 mbar_wait(bar_full(s), ph);
-                if constexpr (KIND == KIND_F16X3) {
+                if (KIND == KIND_F16X3 && p.a_planes) {
+                    // operand tiles were delivered by TMA (async proxy): nothing to convert, just pass the stage on
+                } else if constexpr (KIND == KIND_F16X3) {
                     // A_h = fp16(A), A_l = fp16(A - A_h): thread -> (row, 8-channel group); two 16-byte pieces of the 128B-swizzled
                     // fp32 row in, one 16-byte piece of each 64B-swizzled fp16 row out (both access patterns are conflict-free)
                     const uint8_t* a32 = smem_gen + s * Cfg::STAGE_BYTES;
@@ -530,12 +546,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                         if (chj + 2 < p.sigmoid_ch) o.z = 1.f / (1.f + expf(-o.z));
                         if (chj + 3 < p.sigmoid_ch) o.w = 1.f / (1.f + expf(-o.w));
                     }
-                    *sl = o;
+                    if (KIND == KIND_F16X3 && p.out_planes) {
+                        // two 64-byte-row fp16 tiles in the 16 KB slot (hi | lo), SWIZZLE_64B: this row's 8-byte piece j of the 64-byte line
+                        if (!(fabsf(o.x) < 65504.f) || !(fabsf(o.y) < 65504.f) || !(fabsf(o.z) < 65504.f) || !(fabsf(o.w) < 65504.f)) {
+                            if (p.range_flag && chj < p.cout && row * 128 < p.a_tile_bytes) *p.range_flag = 1;
+                        }
+                        const __half2 h01 = __floats2half2_rn(o.x, o.y), h23 = __floats2half2_rn(o.z, o.w);
+                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                        const __half2 l01 = __floats2half2_rn(o.x - f01.x, o.y - f01.y), l23 = __floats2half2_rn(o.z - f23.x, o.w - f23.y);
+                        const int off = row * 64 + ((((j >> 1) ^ ((row >> 1) & 3)) << 4) | ((j & 1) << 3));
+                        uint2 hv, lv;
+                        hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+                        lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                        *reinterpret_cast<uint2*>(slot_gen + off) = hv;
+                        *reinterpret_cast<uint2*>(slot_gen + Cfg::A_BYTES / 2 + off) = lv;
+                    } else {
+                        *sl = o;
+                    }
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(1 + g, 128);
                 if (et == 0) {
-                    tma_store_4d(&p.tm_d, slot, ch0, w0, h0, n0img);
+                    if (KIND == KIND_F16X3 && p.out_planes) {
+                        tma_store_4d(&p.tm_d, slot, ch0, w0, h0, n0img);
+                        tma_store_4d(&p.tm_d2, slot + Cfg::A_BYTES / 2, ch0, w0, h0, n0img);
+                    } else {
+                        tma_store_4d(&p.tm_d, slot, ch0, w0, h0, n0img);
+                    }
                     tma_store_commit();
                     // free the slot the NEXT chunk will use (its last store must have finished reading shared memory) and start that
                     // chunk's residual load, so that both overlap the next chunk's TMEM reads

@@ -43,7 +43,7 @@ class EngineConfig(ctypes.Structure):
                 ("det_nms_thresh", ctypes.c_float), ("max_dets", ctypes.c_int), ("det_cap", ctypes.c_int),
                 ("use_mask", ctypes.c_int), ("output_prob", ctypes.c_int), ("emit_full_masks", ctypes.c_int),
                 ("passes", ctypes.c_int), ("precise_mask", ctypes.c_int), ("stem_im2col", ctypes.c_int), ("exact_roialign", ctypes.c_int), ("model_type", ctypes.c_int), ("use_rpn", ctypes.c_int),
-                ("conv_kind", ctypes.c_int)]
+                ("conv_kind", ctypes.c_int), ("plane_handover", ctypes.c_int)]
 
 
 _DTYPES = {0: torch.float32, 1: torch.int32, 2: torch.uint8}
@@ -101,6 +101,7 @@ class Engine:
         if conv_kind not in ("f16", "tf32"):
             raise ValueError("conv_kind must be 'f16' or 'tf32'")
         cfg.conv_kind = 0 if conv_kind == "f16" else 1
+        cfg.plane_handover = 0 if os.environ.get("DT_PLANE_HANDOVER", "1") == "0" else 1
         self.cfg = cfg
         self.h = self.L.dt_engine_create(ctypes.byref(cfg))
         if not self.h:

@@ -174,8 +174,9 @@ typedef struct dt_engine_config {
     int model_type;              /* 0 = R-50/101-FPN + RPN (+ '1up4convs' mask head); 1 = R-50/101-C4 (res5 head, 'upshare' mask head) */
     int use_rpn;                 /* C4 only: 1 = Faster/Mask R-CNN (single-level RPN), 0 = Fast R-CNN (caller fills the `rois` buffer) */
     int conv_kind;               /* 0 = three-term product on the kind::f16 pipe (fp16 hi/lo halves, default: twice the tf32 issue rate; an
-                                    activation >= 65504 raises the int32 buffer "range_flag"), 1 = 3xTF32 (no range limit).  The 7x7 stem
-                                    always runs 3xTF32. */
+                                    activation >= 65504 raises the int32 buffer "range_flag"), 1 = 3xTF32 (no range limit) */
+    int plane_handover;          /* kind::f16 only: 1 = conv1 of every bottleneck writes its output as two fp16 planes (hi, lo) that conv2 (3x3)
+                                    loads straight into its operand tiles (no per-tap re-conversion); 0 = fp32 hand-over */
 } dt_engine_config;
 
 typedef void* dt_engine_t;
