@@ -16,12 +16,13 @@
 // previous stage's MMAs run, and B_lo precomputed once per weight tensor.  `passes`==1 runs the
 // plain single-pass TF32 product (debug / speed-of-light reference).
 //
-// KIND_F16X3 (the engine default for every layer but the stem) runs the same three-term product on the kind::f16 pipe, which
+// KIND_F16X3 (the engine default) runs the same three-term product on the kind::f16 pipe, which
 // issues at twice the tf32 rate: A = A_h + A_l with A_h = fp16(A), A_l = fp16(A - A_h) (22 mantissa bits, the same as the two
 // tf32 pieces), B_h / B_l likewise (precomputed, pre-scaled by a power of two so that B_l stays a normal fp16 number; the
 // epilogue scale undoes it exactly).  The fp32 A tile still arrives by TMA; the converter warps write A_h / A_l as two
-// 64-byte-row (SWIZZLE_64B) fp16 tiles.  fp16 has a 5-bit exponent: |A| >= 65504 raises a device flag (the engine then
-// reports it; the tf32 kind has no such limit).
+// 64-byte-row (SWIZZLE_64B) fp16 tiles -- unless the producing layer already wrote the activation as two fp16 planes
+// (a_planes / out_planes: conv1 -> conv2 of a bottleneck), in which case TMA delivers the operand tiles directly.
+// fp16 has a 5-bit exponent: |A| >= 65504 raises a device flag (the engine then reports it; the tf32 kind has no such limit).
 //
 // Tile: BLOCK_M = 128 output pixels (a wbox x hbox x nbox box of the NHWC output, so the same
 // TMA box geometry loads A for any filter tap and stores D, with hardware zero-fill doing the
@@ -39,6 +40,10 @@
 //               run ahead into the next tile while a tile drains.
 // TMEM holds NMAIN rotating main-term accumulators + 1 cross-term accumulator per tile (NMAIN == 0: a single accumulator for
 // both, used by the short-K 256-wide layers), double-buffered when two tiles fit in the 512 columns.
+// Variants selected by the host per layer (conv_host.cuh): 1-SM MMA with multicast weights vs cta_group::2, a K-split over filter
+// taps (tap0 / ntaps), and RING > 0: a ring of residual tiles prefetched by TMA for the short-K residual layers.
+// DT_CONV_EPI_SLOTS (2 staging slots per epilogue group) and DT_CONV_WARPS_NARROW (8 converter warps) are measured-and-rejected
+// experiment switches kept for the next round's tuning.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -48,12 +53,6 @@ namespace dt {
 
 enum ConvResidualMode { RES_NONE = 0, RES_TILE = 1, RES_UPSAMPLE2X = 2 };
 enum ConvKind { KIND_TF32X3 = 0, KIND_F16X3 = 1 };
-// Experiment switch (default off): store the low half of A as bf16 (a byte permute instead of a second fp32->fp16 conversion, which
-// would halve the load on the XU pipe that bounds the converter warps) and run the A_l * B_h term with A = bf16, B = fp16.  The
-// hardware rejects mixed A/B formats inside kind::f16 (illegal instruction on sm_100a), so both halves stay fp16.
-#ifndef DT_CONV_LO_BF16
-#define DT_CONV_LO_BF16 0
-#endif
 #ifndef DT_CONV_EPI_SLOTS
 #define DT_CONV_EPI_SLOTS 1
 #endif
@@ -253,9 +252,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
         constexpr uint32_t idesc_main = umma_idesc(KIND == KIND_F16X3 ? 0 : 2, kTwoSM ? 256 : 128, BLOCK_N);
         // one K step of the instruction = 32 bytes of a row: 8 tf32 or 16 fp16 elements -> 4 or 2 steps per 32-element k-block
         constexpr int KSTEPS = KIND == KIND_F16X3 ? 2 : 4;
-        constexpr uint32_t idesc_al = (KIND == KIND_F16X3 && DT_CONV_LO_BF16) ? umma_idesc2(1, 0, kTwoSM ? 256 : 128, BLOCK_N) : idesc_main;
-        auto mma = [&](uint32_t acc, uint64_t da_, uint64_t db_, uint32_t flag, uint32_t idesc_ = 0xffffffffu) {
-            const uint32_t idesc = idesc_ == 0xffffffffu ? idesc_main : idesc_;
+        auto mma = [&](uint32_t acc, uint64_t da_, uint64_t db_, uint32_t flag) {
+            constexpr uint32_t idesc = idesc_main;
             if constexpr (KIND == KIND_F16X3) {
                 if constexpr (kTwoSM) umma_f16_2sm(acc, da_, db_, idesc, flag); else umma_f16(acc, da_, db_, idesc, flag);
             } else {
@@ -304,7 +302,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                         const uint32_t main_flag = NMAIN == 0 ? ((p.passes == 3 || (kb | k) != 0) ? 1u : 0u) : ((kb >= NMAIN || k != 0) ? 1u : 0u);
                         if (p.passes == 3) {
                             const uint32_t acc_x = acc0 + (uint32_t)(NMAIN * BLOCK_N);
-                            mma(acc_x, dal + koff, dbh + koff, (kb | k) != 0, idesc_al);
+                            mma(acc_x, dal + koff, dbh + koff, (kb | k) != 0);
                             mma(acc_x, da + koff, dbl + koff, 1u);
                         }
                         mma(acc_main, da + koff, dbh + koff, main_flag);
@@ -354,15 +352,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                             const __half h0 = __float2half_rn(f[2 * j]), h1 = __float2half_rn(f[2 * j + 1]);
                             bad = bad || !(fabsf(f[2 * j]) < 65504.f) || !(fabsf(f[2 * j + 1]) < 65504.f);
                             hh[j] = __halves2half2(h0, h1);
-#if DT_CONV_LO_BF16
-                            {
-                                const uint32_t l0 = __float_as_uint(f[2 * j] - __half2float(h0)), l1 = __float_as_uint(f[2 * j + 1] - __half2float(h1));
-                                const uint32_t packed = __byte_perm(l0, l1, 0x7632);      // (l1.hi16 << 16) | l0.hi16: two truncated bf16
-                                ll[j] = *reinterpret_cast<const __half2*>(&packed);
-                            }
-#else
                             ll[j] = __halves2half2(__float2half_rn(f[2 * j] - __half2float(h0)), __float2half_rn(f[2 * j + 1] - __half2float(h1)));
-#endif
                         }
                         const int off = r * 64 + ((c8 ^ ((r >> 1) & 3)) << 4);
                         *reinterpret_cast<uint4*>(ah + off) = *reinterpret_cast<const uint4*>(hh);
