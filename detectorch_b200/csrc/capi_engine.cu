@@ -444,6 +444,8 @@ struct ProgBuilder {
         s.Cout = c.cout; s.kh = c.k; s.kw = c.k; s.pad = kpad; s.stride = stride;
         s.shift = zero_shift ? e->wvec((*cw)["__zeros"].shift) : e->wvec(c.shift);
         s.tap0 = tap0; s.ntaps = ntaps;
+        // mask head: the long-K layers keep the cross terms in their own accumulator (mask logits: 1e-4 absolute bar)
+        s.no_merge = (stage == ST_MASK_HEAD && (ntaps > 0 ? ntaps : c.k * c.k) * (c.cin / 32) > 16) ? 1 : 0;
         if (e->cfg.conv_kind == 0) {
             // kind::f16 three-term product: fp16 halves of w * multiplier(matrix); the multiplier is undone through a per-op scale vector
             const size_t n16 = align_up((size_t)c.cout, 64);

@@ -139,6 +139,7 @@ struct ConvSpec {
     int tap0, ntaps;                              // K-split: only filter taps [tap0, tap0+ntaps) (ntaps == 0: all kh*kw)
     int force_block_n;                            // 0 = auto
     int precise;                                  // BLOCK_N == 128 only: 3 rotating accumulators instead of TMEM double-buffering
+    int no_merge;                                 // keep the cross terms in their own accumulator whatever K is (mask head: tightest parity bar)
 };
 
 inline void choose_box(int Wo, int Ho, int N, int max_w, int* wbox, int* hbox, int* nbox) {
@@ -176,7 +177,7 @@ inline bool conv_use_two_sm(int block_n, int num_kb) {
 
 inline bool conv_merge_acc(int num_kb) {
     static int thr = -1;
-    if (thr < 0) { const char* e = getenv("DT_CONV_MERGE_KB"); thr = e ? atoi(e) : 16; }
+    if (thr < 0) { const char* e = getenv("DT_CONV_MERGE_KB"); thr = e ? atoi(e) : 72; }
     return num_kb <= thr;
 }
 
@@ -268,9 +269,11 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
     p.a_tile_bytes = wbox * hbox * nbox * 128;
     p.relu = s.relu; p.sigmoid_ch = s.sigmoid_ch; p.res_mode = s.res_mode;
     p.passes = s.passes == 1 ? 1 : 3;
-    // 256-wide tiles: (main + cross) accumulators fill the 512 TMEM columns, so the epilogue cannot overlap the next tile; layers with
-    // K <= 512 (where the epilogue is as long as the MMAs, and the accumulation chains are short) use one merged accumulator instead
-    L->nmain = (bn == 64) ? 3 : ((bn == 128 && s.precise) ? 3 : ((bn == 256 && conv_merge_acc(p.ntaps * p.cin_blocks)) ? 0 : 1));
+    // 256-wide tiles: (main + cross) accumulators fill the 512 TMEM columns, so the epilogue cannot overlap the next tile's MMAs.  One
+    // merged accumulator leaves room for two tiles (measured: -0.7 ms per step when applied to every layer up to K = 2304); the price is
+    // a 3x longer truncating-accumulate chain (main and both cross terms in one accumulator), which the trunk / FPN / RPN / box-head
+    // activations can afford (they sit at 1e-5 of their 1e-4 bar) and the mask-head layers cannot (no_merge).
+    L->nmain = (bn == 64) ? 3 : ((bn == 128 && s.precise) ? 3 : ((bn == 256 && !s.no_merge && conv_merge_acc(p.ntaps * p.cin_blocks)) ? 0 : 1));
     finish_grid(L, ceil_div(s.Cout, bn));
     {
         static int use_ring = -1;
