@@ -384,3 +384,43 @@ def test_prep_image_golden_and_full_size(dev):
         sample = preprocess_sample(fpn_on=True)({'image': im, 'dbentry': {'boxes': np.zeros((0, 4), np.float32)}})
         assert sample['scaling_factors'] == scales[0] and tuple(sample['original_im_size'].tolist()) == (h, w, 3)
         assert sample['image'].is_cuda and np.array_equal(sample['image'].cpu().numpy(), want)
+
+
+def test_lib_overlay_modules(built):
+    """The lib/ overlay a reference maintainer puts ahead of the reference's lib/ on sys.path: `cppcuda_cffi.roialign`
+    with the cffi calling convention (caller allocates and zeroes the output / grad_input), `model.detector`, `model.roi_align`,
+    `utils.result_utils`, `utils.preprocess_sample` -- run in a fresh interpreter so the module names cannot collide."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r + "/lib")
+sys.path.insert(0, %r)
+import cppcuda_cffi.roialign as roialign
+from model.detector import detector
+from model.roi_align import RoIAlign
+from utils.result_utils import postprocess_output, segm_results
+from utils.preprocess_sample import preprocess_sample
+from detectorch_b200 import ops
+dev = torch.device("cuda:0")
+g = torch.Generator().manual_seed(0)
+f = torch.randn((1, 8, 20, 30), generator=g).to(dev)
+r = torch.tensor([[0, 10., 12., 200., 150.], [0, 50., 60., 90., 300.], [0, 0., 0., 479., 319.]]).to(dev)
+out = torch.zeros((3, 8, 7, 7), device=dev)
+assert roialign.roi_align_forward_cuda(f, r, out, 7, 7, 1 / 16., 2) == 1
+assert torch.equal(out, ops.roi_align_forward_nchw(f, r, 7, 7, 1 / 16., 2))
+go = torch.randn((3, 8, 7, 7), generator=g).to(dev)
+gi = torch.zeros((1, 8, 20, 30), device=dev)
+assert roialign.roi_align_backward_cuda(r, go, gi, 7, 7, 1 / 16., 2) == 1
+want = ops.roi_align_backward_nchw(r, go, (1, 8, 20, 30), 7, 7, 1 / 16., 2)
+assert float((gi - want).abs().max()) <= 1e-5 * max(1.0, float(want.abs().max()))
+try:
+    roialign.roi_align_forward_cpu(f.cpu(), r.cpu(), out.cpu(), 7, 7, 1 / 16., 2)
+    raise SystemExit("the overlay must not have a CPU path")
+except RuntimeError:
+    pass
+print("OVERLAY OK")
+''' % (root, root)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "OVERLAY OK" in out.stdout, out.stderr[-2000:]

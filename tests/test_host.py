@@ -95,3 +95,17 @@ def test_product_path_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(root, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("parity oracle", ""), f
+
+
+def test_lib_overlay_imports(built):
+    """The reference-facing overlay (lib/) resolves `cppcuda_cffi.roialign`, `model.detector`, `model.roi_align`,
+    `utils.result_utils`, `utils.preprocess_sample` to this package (fresh interpreter: the names must not collide with anything)."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r + '/lib'); sys.path.insert(0, %r)\n"
+            "import cppcuda_cffi.roialign as r, model.detector as d, model.roi_align as a, utils.result_utils as u, utils.preprocess_sample as p\n"
+            "assert all(hasattr(r, n) for n in ('roi_align_forward_cuda', 'roi_align_backward_cuda', 'roi_align_forward_cpu'))\n"
+            "assert hasattr(d, 'detector') and hasattr(a, 'RoIAlignFunction') and hasattr(u, 'postprocess_output') and hasattr(u, 'segm_results')\n"
+            "assert hasattr(p, 'preprocess_sample'); print('OVERLAY IMPORTS OK')\n") % (ROOT, ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "OVERLAY IMPORTS OK" in out.stdout, out.stderr[-1500:]
