@@ -109,3 +109,25 @@ def test_lib_overlay_imports(built):
             "assert hasattr(p, 'preprocess_sample'); print('OVERLAY IMPORTS OK')\n") % (ROOT, ROOT)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "OVERLAY IMPORTS OK" in out.stdout, out.stderr[-1500:]
+
+
+def test_host_side_helpers():
+    """Host logic of the new entry points: the prep_im_for_blob scale rule (blob.py:67-76) and the power-of-two weight pre-scale
+    of the kind::f16 convolutions."""
+    from detectorch_b200.utils.blob import im_scale_for
+    from detectorch_b200 import ops
+    from oracle import ref
+    rng = np.random.RandomState(0)
+    for (h, w) in [(480, 640), (375, 1242), (1600, 2000), (64, 48), (800, 1216), (333, 500)]:
+        im = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        # the oracle restatement (pinned to the reference's blob.py) gives the scale; skip its resize for the big images
+        want = ref.prep_im_for_blob(im, target_sizes=[800], max_size=1333)[1][0] if h * w < 400000 else None
+        got = im_scale_for((h, w, 3), 800, 1333)
+        if want is not None:
+            assert got == want
+        assert np.round(got * max(h, w)) <= 1333 + 1e-9 and (abs(got * min(h, w) - 800) < 1e-9 or abs(got * max(h, w) - 1333) < 1e-9)
+    for m in (3e-4, 0.02, 0.7, 1.0, 5.5, 300.0):
+        w_ = torch.tensor([m, -m / 3, 0.0])
+        mult = ops.weight_multiplier(w_)
+        assert 2.0 ** 13 <= m * mult < 2.0 ** 14 and np.log2(mult) == int(np.log2(mult))
+    assert ops.weight_multiplier(torch.zeros(4)) == 1.0
