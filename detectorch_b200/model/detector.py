@@ -302,8 +302,10 @@ class detector(torch.nn.Module):
         with_masks = self.use_mask_head if with_masks is None else with_masks
         eng.run(images.contiguous().float(), float(scaling_factor), ST_TRUNK, ST_MASK_OUT if with_masks else ST_DETECT)
         B, cap = images.size(0), eng.cfg.det_cap
+        # "range_flag" (int32 [1]) is non-zero if an activation left the fp16 range of the default kind::f16 convolutions: read it together
+        # with the results (no extra synchronisation here), or call self._engine.check_range()
         out = {"boxes": eng.buffer("det_boxes"), "scores": eng.buffer("det_scores"), "classes": eng.buffer("det_classes"),
-               "counts": eng.buffer("det_counts"), "roi_idx": eng.buffer("det_roi_idx")}
+               "counts": eng.buffer("det_counts"), "roi_idx": eng.buffer("det_roi_idx"), "range_flag": eng.buffer("range_flag")}
         if with_masks:
             out["masks"] = eng.buffer("masks").view(B, cap, 28, 28)
         return out
