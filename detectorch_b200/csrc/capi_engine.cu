@@ -291,8 +291,8 @@ void build_param_table(Engine* e, std::map<std::string, ConvW>* cw) {
         bias_conv("conv_body.fpn_lateral." + std::to_string(i), 256, cins[i], 1);
         bias_conv("conv_body.fpn_output." + std::to_string(i), 256, 256, 3);
     }
-    bias_conv("rpn.conv_rpn", 256, 256, 3);
-    {   // fused RPN 1x1: rows [0,3) objectness, [3,15) deltas, row 15 zero
+    if (e->cfg.use_rpn) bias_conv("rpn.conv_rpn", 256, 256, 3);
+    if (e->cfg.use_rpn) {   // fused RPN 1x1: rows [0,3) objectness, [3,15) deltas, row 15 zero
         ConvW c; c.cout = 16; c.cin = 256; c.k = 1;
         c.w = add_mat(e, "rpn.rpn_cls_prob.weight", PK_ROWS_W, 16, 256, 3, 256, 0, 0);
         e->params["rpn.rpn_cls_prob.weight"].row_off = 0;
@@ -382,20 +382,22 @@ void plan_buffers(Engine* e) {
         add_buf(e, "P" + std::to_string(i + 2), {B, e->LH[i], e->LW[i], 256});
     }
     add_buf(e, "P6", {B, e->LH[4], e->LW[4], 256});
-    long long anchors_total = 0;
-    for (int i = 0; i < 5; ++i) {
-        add_buf(e, "rpn_t" + std::to_string(i + 2), {B, e->LH[i], e->LW[i], 256});
-        add_buf(e, "rpn_out" + std::to_string(i + 2), {B, e->LH[i], e->LW[i], 16});
-        anchors_total += (long long)e->LH[i] * e->LW[i] * 3;
-    }
     const int L = 5, pre = c.pre_nms_top_n, post = c.post_nms_top_n;
-    add_buf(e, "rpn_k0", {B, anchors_total}, 1); add_buf(e, "rpn_k1", {B, anchors_total}, 1);
-    add_buf(e, "rpn_v0", {B, anchors_total}, 1); add_buf(e, "rpn_v1", {B, anchors_total}, 1);
-    add_buf(e, "rpn_cand", {B, L, pre, 4}); add_buf(e, "rpn_cand_score", {B, L, pre});
-    add_buf(e, "rpn_order", {B, L, pre}, 1);
-    add_buf(e, "props", {B, L, post, 4}); add_buf(e, "prop_scores", {B, L, post}); add_buf(e, "prop_counts", {B, L}, 1);
-    add_buf(e, "col_k0", {B, L * post}, 1); add_buf(e, "col_k1", {B, L * post}, 1);
-    add_buf(e, "col_v0", {B, L * post}, 1); add_buf(e, "col_v1", {B, L * post}, 1);
+    if (c.use_rpn) {       // Fast R-CNN with the FPN body (eval_fast_FPN.ipynb) has no RPN: the caller fills `rois` / `roi_levels` / `roi_counts`
+        long long anchors_total = 0;
+        for (int i = 0; i < 5; ++i) {
+            add_buf(e, "rpn_t" + std::to_string(i + 2), {B, e->LH[i], e->LW[i], 256});
+            add_buf(e, "rpn_out" + std::to_string(i + 2), {B, e->LH[i], e->LW[i], 16});
+            anchors_total += (long long)e->LH[i] * e->LW[i] * 3;
+        }
+        add_buf(e, "rpn_k0", {B, anchors_total}, 1); add_buf(e, "rpn_k1", {B, anchors_total}, 1);
+        add_buf(e, "rpn_v0", {B, anchors_total}, 1); add_buf(e, "rpn_v1", {B, anchors_total}, 1);
+        add_buf(e, "rpn_cand", {B, L, pre, 4}); add_buf(e, "rpn_cand_score", {B, L, pre});
+        add_buf(e, "rpn_order", {B, L, pre}, 1);
+        add_buf(e, "props", {B, L, post, 4}); add_buf(e, "prop_scores", {B, L, post}); add_buf(e, "prop_counts", {B, L}, 1);
+        add_buf(e, "col_k0", {B, L * post}, 1); add_buf(e, "col_k1", {B, L * post}, 1);
+        add_buf(e, "col_v0", {B, L * post}, 1); add_buf(e, "col_v1", {B, L * post}, 1);
+    }
     add_buf(e, "rois", {B, post, 5}); add_buf(e, "roi_levels", {B, post}, 1); add_buf(e, "roi_counts", {B}, 1);
     add_buf(e, "roi_feat", {(long long)B * post, 7, 7, 256});
     add_buf(e, "fc6", {(long long)B * post, 1024}); add_buf(e, "fc7", {(long long)B * post, 1024});
@@ -666,14 +668,14 @@ bool build_program(Engine* e, std::map<std::string, ConvW>* cw) {
                 e->buf("P" + std::to_string(i + 2)), 256, 1, 1, false);
     pb.fn(ST_FPN, fn_p6);
     // ---- RPN head on P2..P6 (detector.py:251)
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < 5 && c.use_rpn; ++i) {
         const std::string L = std::to_string(i + 2);
         pb.conv(ST_RPN, "rpn.conv_rpn", e->buf("P" + L), B, e->LH[i], e->LW[i], 256, e->buf("rpn_t" + L), 256, 1, 1, true);
         pb.conv(ST_RPN, "rpn.head", e->buf("rpn_t" + L), B, e->LH[i], e->LW[i], 256, e->buf("rpn_out" + L), 16, 0, 1, false, RES_NONE, nullptr,
                 nullptr, 0, 0, 3);
     }
     // ---- proposals (generate_proposals.py) + collect (collect_and_distribute...py)
-    {
+    if (c.use_rpn) {
         RpnParams& P = e->rpn;
         memset(&P, 0, sizeof(P));
         P.num_levels = 5; P.B = B;
@@ -824,7 +826,7 @@ dt_engine_t dt_engine_create(const dt_engine_config* cfg) {
     if (e->cfg.passes != 1) e->cfg.passes = 3;
     std::map<std::string, ConvW> cw;
     if (e->cfg.model_type == 1) { build_param_table_c4(e, &cw); plan_buffers_c4(e); }
-    else { e->cfg.use_rpn = 1; build_param_table(e, &cw); plan_buffers(e); }
+    else { build_param_table(e, &cw); plan_buffers(e); }
     return e;
 }
 
@@ -836,16 +838,16 @@ int64_t dt_engine_weight_bytes(dt_engine_t h) {
 }
 int64_t dt_engine_workspace_bytes(dt_engine_t h) { return (int64_t)reinterpret_cast<Engine*>(h)->ws_bytes; }
 
-int dt_engine_bind(dt_engine_t h, void* weights, void* workspace, dt_stream_t stream) {
-    Engine* e = reinterpret_cast<Engine*>(h);
+static int bind_impl(Engine* e, void* weights, void* workspace, cudaStream_t st, bool fresh) {
     e->wbase = reinterpret_cast<float*>(weights);
     e->ws = reinterpret_cast<uint8_t*>(workspace);
-    cudaStream_t st = (cudaStream_t)stream;
-    DT_CHECK_CUDA(cudaMemsetAsync(weights, 0, (2 * e->mat_floats + e->vec_floats) * sizeof(float), st));
-    // the shared all-ones scale vector sits at the start of the vector region
-    fill_kernel<<<8, 256, 0, st>>>(e->wvec(0), 2048, 1.f);
-    if (e->cfg.model_type != 1) fill_kernel<<<8, 256, 0, st>>>(e->wvec(2048), 2048, 0.f);
-    DT_CHECK_CUDA(cudaGetLastError());
+    if (fresh) {
+        DT_CHECK_CUDA(cudaMemsetAsync(weights, 0, (2 * e->mat_floats + e->vec_floats) * sizeof(float), st));
+        // the shared all-ones scale vector sits at the start of the vector region
+        fill_kernel<<<8, 256, 0, st>>>(e->wvec(0), 2048, 1.f);
+        if (e->cfg.model_type != 1) fill_kernel<<<8, 256, 0, st>>>(e->wvec(2048), 2048, 0.f);
+        DT_CHECK_CUDA(cudaGetLastError());
+    }
     e->ops.clear();
     e->scale16_used = 0;
     e->fns.clear();
@@ -857,6 +859,21 @@ int dt_engine_bind(dt_engine_t h, void* weights, void* workspace, dt_stream_t st
     }
     if (!(e->cfg.model_type == 1 ? build_program_c4(e, &cw) : build_program(e, &cw))) return 0;
     e->bound = true;
+    return 1;
+}
+
+int dt_engine_bind(dt_engine_t h, void* weights, void* workspace, dt_stream_t stream) {
+    return bind_impl(reinterpret_cast<Engine*>(h), weights, workspace, (cudaStream_t)stream, true);
+}
+
+// Bind to a weight buffer that ANOTHER engine of the same model configuration (everything in dt_engine_config except batch / height /
+// width) has already loaded and finalised: the packed weights, their fp16 halves and the per-launch scale vectors do not depend on the
+// input shape, so engines for different image sizes share one copy (the notebook flow meets dozens of padded sizes).  Nothing is
+// written to `loaded_weights`; every parameter counts as loaded.
+int dt_engine_attach(dt_engine_t h, void* loaded_weights, void* workspace, dt_stream_t stream) {
+    Engine* e = reinterpret_cast<Engine*>(h);
+    if (!bind_impl(e, loaded_weights, workspace, (cudaStream_t)stream, false)) return 0;
+    for (auto& kv : e->params) kv.second.loaded = true;
     return 1;
 }
 

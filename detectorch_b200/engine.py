@@ -3,6 +3,7 @@ Torch only provides the two flat device buffers, the stream and zero-copy views 
 engine tensors; every kernel is launched by the C++ side."""
 import ctypes
 import os
+import weakref
 
 import torch
 
@@ -58,6 +59,7 @@ def _bind_engine_api(L):
     L.dt_engine_weight_bytes.restype, L.dt_engine_weight_bytes.argtypes = c64, [vp]
     L.dt_engine_workspace_bytes.restype, L.dt_engine_workspace_bytes.argtypes = c64, [vp]
     L.dt_engine_bind.restype, L.dt_engine_bind.argtypes = ci, [vp, vp, vp, vp]
+    L.dt_engine_attach.restype, L.dt_engine_attach.argtypes = ci, [vp, vp, vp, vp]
     L.dt_engine_load_param.restype, L.dt_engine_load_param.argtypes = ci, [vp, ctypes.c_char_p, vp, c64, vp]
     L.dt_engine_finalize_weights.restype, L.dt_engine_finalize_weights.argtypes = ci, [vp, vp]
     L.dt_engine_buffer.restype = ci
@@ -72,10 +74,55 @@ def _bind_engine_api(L):
     L._engine_bound = True
 
 
+_live_engines = weakref.WeakSet()
+
+
+def engine_owning(*tensors):
+    """The live Engine whose workspace contains one of the given CUDA tensors (views of engine buffers returned by the mirror API), else None.
+    This is how postprocess_output / mask_head find the engine that produced their inputs without any global "active engine" state."""
+    for t in tensors:
+        if isinstance(t, (list, tuple)):
+            e = engine_owning(*t)
+            if e is not None:
+                return e
+            continue
+        if not torch.is_tensor(t) or not t.is_cuda or t.numel() == 0:
+            continue
+        p = t.data_ptr()
+        for e in list(_live_engines):
+            if e.device == t.device and e.owns(p):
+                return e
+    return None
+
+
+def fold_bn_running_stats(sd, eps=1e-5):
+    """The engine folds eval-mode BatchNorm as gamma / sqrt(1 + eps), beta -- the reference's situation (detector.py:231,301: the Detectron
+    import never touches the running stats, so they stay at (0, 1)).  A state_dict with NON-trivial running_mean / running_var (a
+    torchvision-pretrained trunk, a checkpoint trained with live BN) is re-expressed in that form here, so that the result equals what
+    torch's eval BatchNorm computes: gamma' = gamma * sqrt(1 + eps) / sqrt(var + eps), beta' = beta - mean * gamma / sqrt(var + eps)."""
+    out = dict(sd)
+    for k, mean in sd.items():
+        if not k.endswith(".running_mean"):
+            continue
+        pre = k[:-len(".running_mean")]
+        var = sd.get(pre + ".running_var")
+        if var is None or (pre + ".weight") not in sd or (pre + ".bias") not in sd:
+            continue
+        mean, var = mean.detach().double(), var.detach().double()
+        if bool((mean == 0).all()) and bool((var == 1).all()):
+            continue
+        g, b = sd[pre + ".weight"].detach().double().to(mean.device), sd[pre + ".bias"].detach().double().to(mean.device)
+        inv = 1.0 / torch.sqrt(var + eps)
+        out[pre + ".weight"] = (g * inv * (1.0 + eps) ** 0.5).float()
+        out[pre + ".bias"] = (b - mean * g * inv).float()
+    return out
+
+
 class Engine:
     def __init__(self, arch="resnet50", batch=1, height=800, width=1216, pre_nms_top_n=1000, post_nms_top_n=1000,
                  rpn_nms_thresh=0.7, rpn_min_size=0.0, num_classes=81, score_thresh=0.05, det_nms_thresh=0.5, max_dets=100,
-                 det_cap=100, use_mask=True, output_prob=True, emit_full_masks=False, passes=3, precise_mask=True, stem_im2col=False, exact_roialign=False, model="fpn", use_rpn=True, conv_kind=None, device="cuda:0"):
+                 det_cap=100, use_mask=True, output_prob=True, emit_full_masks=False, passes=3, precise_mask=True, stem_im2col=False, exact_roialign=False, model="fpn", use_rpn=True, conv_kind=None, device="cuda:0",
+                 share_weights_with=None):
         if not torch.cuda.is_available():
             raise RuntimeError("detectorch_b200.Engine needs a CUDA device (no CPU fallback)")
         self.L = _lib.lib()
@@ -104,12 +151,34 @@ class Engine:
         self.h = self.L.dt_engine_create(ctypes.byref(cfg))
         if not self.h:
             raise RuntimeError("dt_engine_create failed (see stderr)")
-        with torch.cuda.device(self.device):
-            self.weights = torch.empty((self.L.dt_engine_weight_bytes(self.h),), dtype=torch.uint8, device=self.device)
-            self.workspace = torch.zeros((self.L.dt_engine_workspace_bytes(self.h),), dtype=torch.uint8, device=self.device)
-            _lib.check(self.L.dt_engine_bind(self.h, self.weights.data_ptr(), self.workspace.data_ptr(), self._stream()), "dt_engine_bind")
         self._views = {}
         self.weights_loaded = False
+        with torch.cuda.device(self.device):
+            self.workspace = torch.zeros((self.L.dt_engine_workspace_bytes(self.h),), dtype=torch.uint8, device=self.device)
+            self._ws_lo = self.workspace.data_ptr()
+            self._ws_hi = self._ws_lo + self.workspace.numel()
+            if share_weights_with is not None:
+                # packed weights do not depend on the input shape: engines of one model for different image sizes share one copy
+                o = share_weights_with
+                if self.model_key() != o.model_key() or not o.weights_loaded or o.device != self.device or \
+                        self.L.dt_engine_weight_bytes(self.h) != o.weights.numel():
+                    raise RuntimeError("share_weights_with: the other engine must hold loaded weights of the same model configuration on the same device")
+                self.weights = o.weights
+                _lib.check(self.L.dt_engine_attach(self.h, self.weights.data_ptr(), self.workspace.data_ptr(), self._stream()), "dt_engine_attach")
+                self.weights_loaded = True
+            else:
+                self.weights = torch.empty((self.L.dt_engine_weight_bytes(self.h),), dtype=torch.uint8, device=self.device)
+                _lib.check(self.L.dt_engine_bind(self.h, self.weights.data_ptr(), self.workspace.data_ptr(), self._stream()), "dt_engine_bind")
+        _live_engines.add(self)
+
+    def model_key(self):
+        """Everything in the configuration that shapes the packed weight buffer / launch sequence -- all of it except batch, height, width."""
+        c = self.cfg
+        skip = ("batch", "height", "width", "arch_blocks")
+        return tuple(c.arch_blocks) + tuple(getattr(c, f) for f, _ in c._fields_ if f not in skip)
+
+    def owns(self, ptr):
+        return self._ws_lo <= ptr < self._ws_hi
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -123,18 +192,24 @@ class Engine:
             pass
 
     def load_state_dict(self, sd):
-        """sd: {reference state_dict name: tensor}.  Names that are not hot-path parameters are ignored."""
+        """sd: {reference state_dict name: tensor}.  Names that are not hot-path parameters are ignored; BatchNorm running statistics other
+        than (0, 1) are folded into the affine pair (fold_bn_running_stats)."""
         n = 0
-        for name, t in sd.items():
-            if not torch.is_tensor(t) or not t.dtype.is_floating_point:
-                continue
-            t = t.detach().to(self.device, torch.float32).contiguous()
-            r = self.L.dt_engine_load_param(self.h, name.encode(), t.data_ptr(), t.numel(), self._stream())
-            if r == 0:
-                raise RuntimeError("dt_engine_load_param(%s) failed" % name)
-            n += (r == 1)
-            torch.cuda.current_stream(self.device).synchronize()   # keep `t` alive until the pack kernel ran
-        _lib.check(self.L.dt_engine_finalize_weights(self.h, self._stream()), "dt_engine_finalize_weights")
+        sd = fold_bn_running_stats({k: v for k, v in sd.items() if torch.is_tensor(v) and v.dtype.is_floating_point})
+        staged = []                                                # keeps the device copies alive until the pack kernels ran
+        with torch.cuda.device(self.device):
+            for name, t in sd.items():
+                if name.endswith((".running_mean", ".running_var")):
+                    continue
+                t = t.detach().to(self.device, torch.float32).contiguous()
+                r = self.L.dt_engine_load_param(self.h, name.encode(), t.data_ptr(), t.numel(), self._stream())
+                if r == 0:
+                    raise RuntimeError("dt_engine_load_param(%s) failed" % name)
+                n += (r == 1)
+                staged.append(t)
+            _lib.check(self.L.dt_engine_finalize_weights(self.h, self._stream()), "dt_engine_finalize_weights")
+            torch.cuda.current_stream(self.device).synchronize()
+        del staged
         self.weights_loaded = True
         return n
 
@@ -167,7 +242,8 @@ class Engine:
             if tuple(image.shape) != (self.cfg.batch, 3, self.cfg.height, self.cfg.width):
                 raise RuntimeError("image shape %s does not match the engine (%d,3,%d,%d)" % (tuple(image.shape), self.cfg.batch, self.cfg.height, self.cfg.width))
             ptr = image.data_ptr()
-        _lib.check(self.L.dt_engine_run(self.h, ptr, float(scaling_factor), int(first), int(last), self._stream()), "dt_engine_run")
+        with torch.cuda.device(self.device):       # the C ABI launches on the current device: make it the engine's
+            _lib.check(self.L.dt_engine_run(self.h, ptr, float(scaling_factor), int(first), int(last), self._stream()), "dt_engine_run")
 
     def check_range(self):
         """kind::f16 convs raise a device flag when an activation does not fit fp16 (|x| >= 65504).  Synchronises; raises if set."""
@@ -184,7 +260,8 @@ class Engine:
         """One event-bracketed pass: list of (ms, algorithmic_flops, stage, block_n) per launch."""
         cap = 512
         ms = (ctypes.c_float * cap)(); fl = (ctypes.c_double * cap)(); st = (ctypes.c_int * cap)(); bn = (ctypes.c_int * cap)()
-        n = self.L.dt_engine_profile(self.h, image.data_ptr(), float(scaling_factor), first, last, self._stream(), ms, fl, st, bn, cap)
+        with torch.cuda.device(self.device):
+            n = self.L.dt_engine_profile(self.h, image.data_ptr(), float(scaling_factor), first, last, self._stream(), ms, fl, st, bn, cap)
         if n <= 0:
             raise RuntimeError("dt_engine_profile failed")
         return [(ms[i], fl[i], st[i], bn[i]) for i in range(n)]

@@ -7,15 +7,40 @@ Detectron-pkl loader entry point -- but forward() runs the fused sm_100a engine
 The torch modules below are PARAMETER CONTAINERS ONLY (so state_dict()/load_state_dict()/the pkl
 loader keep working); none of their forward() methods is ever called.
 
-Supported configuration this round: the FPN + RPN (+ '1up4convs' mask head) family
-(eval_faster_FPN.ipynb / eval_mask_FPN.ipynb constructor kwargs), ResNet-50/101.
+Supported configurations = the constructor kwargs of the reference's eight eval_*.ipynb notebooks, ResNet-50/101:
+  FPN family  eval_fast_FPN (pre-computed per-level proposals), eval_faster_FPN, eval_mask_FPN ('1up4convs')
+  C4 family   eval_fast (pre-computed proposals), eval_faster, eval_mask ('upshare')
+
+Aliasing: forward() returns zero-copy VIEWS of engine buffers (cls_score, bbox_pred, rois, the FPN maps); they are overwritten by the
+next forward() on an engine of the same input shape.  Clone what must outlive the next image (the notebooks do not).
+Weights: engines pack the parameters when they are created; call load_state_dict / load_pretrained_weights (or bump
+`model._weights_version`) after editing parameters in place.
 """
 import numpy as np
 import torch
 import torchvision.models as models
 
-from ..engine import Engine, ST_TRUNK, ST_ROI_BOX, ST_BOX_HEAD, ST_DETECT, ST_MASK_ROI_FEAT, ST_MASK_OUT
-from ..utils import result_utils as _result_utils
+import collections
+import os
+
+from ..engine import Engine, engine_owning, ST_TRUNK, ST_FPN, ST_ROI_BOX, ST_BOX_HEAD, ST_DETECT, ST_MASK_ROI_FEAT, ST_MASK_OUT
+
+
+def caffe2_blob_name(key):
+    """torchvision ResNet state_dict key -> Detectron (caffe2) blob name, the mapping utils/utils.py:44-71 (parse_th_to_caffe2) implements:
+    conv1.weight -> conv1_w; bn1.{weight,bias} -> res_conv1_bn_{s,b}; layerL.B.convK.weight -> res{L+1}_{B}_branch2{a,b,c}_w;
+    layerL.B.bnK.{weight,bias} -> res{L+1}_{B}_branch2{a,b,c}_bn_{s,b}; layerL.B.downsample.{0.weight,1.weight,1.bias} -> res{L+1}_{B}_branch1_{w,bn_s,bn_b}."""
+    t = key.split('.')
+    leaf = {'weight': '_s', 'bias': '_b'}
+    if t[0] == 'conv1':
+        return 'conv1_w'
+    if t[0] == 'bn1':
+        return 'res_conv1_bn' + leaf[t[1]]
+    stage = 'res%d_%s' % (int(t[0][-1]) + 1, t[1])
+    if t[2] == 'downsample':
+        return stage + '_branch1' + ('_w' if t[3] == '0' else '_bn' + leaf[t[4]])
+    branch = stage + '_branch2' + 'abc'[int(t[2][-1]) - 1]
+    return branch + ('_w' if t[2].startswith('conv') else '_bn' + leaf[t[3]])
 
 
 class _FpnBody(torch.nn.Module):           # parameter container: detector.py:12-33
@@ -100,16 +125,16 @@ class detector(torch.nn.Module):
         self.use_two_layer_mlp_head = conv_head_layers == 'two_layer_mlp'
         self.output_prob = output_prob
         self.N_classes = N_classes
-        fpn_ok = (self.use_fpn_body and self.use_rpn_head and self.use_two_layer_mlp_head and fpn_extra_lvl and
+        fpn_ok = (self.use_fpn_body and self.use_two_layer_mlp_head and (fpn_extra_lvl or not use_rpn_head) and
                   list(fpn_layers) == ['layer1', 'layer2', 'layer3', 'layer4'] and self.roi_height == 7 and self.roi_width == 7 and
                   self.roi_sampling_ratio == 2 and self.roi_spatial_scale == [0.25, 0.125, 0.0625, 0.03125] and
-                  (not use_mask_head or mask_head_type == '1up4convs'))
+                  (not use_mask_head or (mask_head_type == '1up4convs' and use_rpn_head)))
         c4_ok = (not self.use_fpn_body and list(conv_body_layers) == ['conv1', 'bn1', 'relu', 'maxpool', 'layer1', 'layer2', 'layer3'] and
                  list(conv_head_layers) == ['layer4', 'avgpool'] and self.roi_height == 14 and self.roi_width == 14 and
                  self.roi_sampling_ratio == 0 and self.roi_spatial_scale == 0.0625 and (not use_mask_head or mask_head_type == 'upshare'))
         if not ((fpn_ok or c4_ok) and arch in ('resnet50', 'resnet101') and not train):
             raise NotImplementedError("detectorch_b200 implements the reference's inference configurations (eval_*.ipynb kwargs): "
-                                      "R-50/101-FPN + RPN (+1up4convs mask) and R-50/101-C4 Fast/Faster/Mask (upshare); got something else")
+                                      "R-50/101-FPN Fast/Faster/Mask (1up4convs) and R-50/101-C4 Fast/Faster/Mask (upshare); got something else")
         self.family = "fpn" if fpn_ok else "c4"
         if arch.startswith('resnet'):
             self.model = getattr(models, arch)()
@@ -118,7 +143,8 @@ class detector(torch.nn.Module):
         if self.family == "fpn":
             self.conv_body = _FpnBody(torch.nn.Sequential(*[getattr(self.model, l) for l in conv_body_layers]), (256, 512, 1024, 2048), fpn_layers)
             self.conv_head = _TwoLayerMlp()
-            self.rpn = _RpnHead(256, 256, 3)
+            if self.use_rpn_head:
+                self.rpn = _RpnHead(256, 256, 3)
             feat = 1024      # two-layer MLP head (detector.py:143,212: the 2048 default only fits the C4 head)
         else:
             self.conv_body = torch.nn.Sequential(*[getattr(self.model, l) for l in conv_body_layers])
@@ -130,8 +156,8 @@ class detector(torch.nn.Module):
         self.classif_head = torch.nn.Linear(feat, N_classes)
         if self.use_mask_head:
             self.mask_head = _MaskHead(self, output_prob, None if self.family == "fpn" else self.conv_head[0])
-        self._engines = {}
-        self._engine = None
+        self._engines = collections.OrderedDict()      # LRU: (batch, h, w, overrides) -> (Engine, weights_version)
+        self.max_cached_engines = int(os.environ.get("DT_ENGINE_CACHE", "6"))
         self._weights_version = 0
         if detector_pkl_file is not None:
             self.load_pretrained_weights(detector_pkl_file, model='detector')
@@ -141,10 +167,8 @@ class detector(torch.nn.Module):
 
     # ------------------------------------------------------------------ weights
     def load_pretrained_weights(self, caffe_pkl_file, model='detector'):
-        """Detectron caffe2-pickle import (detector.py:289-374).  'Next' row of SURVEY.md 8f; needs
-        utils.utils.parse_th_to_caffe2 from the reference tree on sys.path."""
+        """Detectron caffe2-pickle import (detector.py:289-374), 'next' row of SURVEY.md 8f."""
         import pickle
-        from utils.utils import parse_th_to_caffe2   # reference helper (utils/utils.py:44-71)
         with open(caffe_pkl_file, 'rb') as f:
             blobs = pickle.load(f, encoding='latin1')
         if model == 'detector':
@@ -153,7 +177,7 @@ class detector(torch.nn.Module):
         for k in sd.keys():
             if 'running' in k or 'fc' in k or 'num_batches' in k:
                 continue
-            kc = parse_th_to_caffe2(k.split('.'))
+            kc = caffe2_blob_name(k)
             w = torch.FloatTensor(blobs[kc])
             sd[k] = w[:, (2, 1, 0), :, :] if k == 'conv1.weight' else w     # BGR -> RGB
         self.model.load_state_dict(sd)
@@ -161,21 +185,27 @@ class detector(torch.nn.Module):
             def put(mod, wn, bn):
                 mod.weight.data = torch.FloatTensor(blobs[wn]); mod.bias.data = torch.FloatTensor(blobs[bn])
             put(self.bbox_head, 'bbox_pred_w', 'bbox_pred_b'); put(self.classif_head, 'cls_score_w', 'cls_score_b')
-            put(self.rpn.conv_rpn, 'conv_rpn_fpn2_w', 'conv_rpn_fpn2_b')
-            put(self.rpn.rpn_cls_prob, 'rpn_cls_logits_fpn2_w', 'rpn_cls_logits_fpn2_b')
-            put(self.rpn.rpn_bbox_pred, 'rpn_bbox_pred_fpn2_w', 'rpn_bbox_pred_fpn2_b')
+            # the blob names depend on the configuration exactly as in detector.py:317-374
+            if self.use_rpn_head:
+                sfx = '_fpn2' if self.use_fpn_body else ''
+                put(self.rpn.conv_rpn, 'conv_rpn%s_w' % sfx, 'conv_rpn%s_b' % sfx)
+                put(self.rpn.rpn_cls_prob, 'rpn_cls_logits%s_w' % sfx, 'rpn_cls_logits%s_b' % sfx)
+                put(self.rpn.rpn_bbox_pred, 'rpn_bbox_pred%s_w' % sfx, 'rpn_bbox_pred%s_b' % sfx)
             if self.use_mask_head:
                 put(self.mask_head.transposed_conv, 'conv5_mask_w', 'conv5_mask_b')
                 put(self.mask_head.classif_logits, 'mask_fcn_logits_w', 'mask_fcn_logits_b')
-                for i in range(1, 5):
-                    put(getattr(self.mask_head.conv_head, 'fcn%d' % i), '_[mask]_fcn%d_w' % i, '_[mask]_fcn%d_b' % i)
-            for i, l in enumerate(self.conv_body.fpn_layers):
-                kc = parse_th_to_caffe2((l + '.' + list(getattr(self.model, l).state_dict().keys())[-1]).split('.'))
-                kc = kc[:kc.rfind("_")]
-                suffix = '_sum_lateral' if i < len(self.conv_body.fpn_layers) - 1 else '_sum'
-                put(self.conv_body.fpn_lateral[i], 'fpn_inner_' + kc + suffix + '_w', 'fpn_inner_' + kc + suffix + '_b')
-                put(self.conv_body.fpn_output[i], 'fpn_' + kc + '_sum_w', 'fpn_' + kc + '_sum_b')
-            put(self.conv_head.fc6, 'fc6_w', 'fc6_b'); put(self.conv_head.fc7, 'fc7_w', 'fc7_b')
+                if self.mask_head_type == '1up4convs':
+                    for i in range(1, 5):
+                        put(getattr(self.mask_head.conv_head, 'fcn%d' % i), '_[mask]_fcn%d_w' % i, '_[mask]_fcn%d_b' % i)
+            if self.use_fpn_body:
+                for i, l in enumerate(self.conv_body.fpn_layers):
+                    # the FPN blobs are named after the last conv of the stage's last block, e.g. fpn_inner_res5_2_sum (detector.py:357-359)
+                    kc = 'res%d_%d' % (int(l[-1]) + 1, len(getattr(self.model, l)) - 1)
+                    suffix = '_sum_lateral' if i < len(self.conv_body.fpn_layers) - 1 else '_sum'
+                    put(self.conv_body.fpn_lateral[i], 'fpn_inner_' + kc + suffix + '_w', 'fpn_inner_' + kc + suffix + '_b')
+                    put(self.conv_body.fpn_output[i], 'fpn_' + kc + '_sum_w', 'fpn_' + kc + '_sum_b')
+            if self.use_two_layer_mlp_head:
+                put(self.conv_head.fc6, 'fc6_w', 'fc6_b'); put(self.conv_head.fc7, 'fc7_w', 'fc7_b')
         self._weights_version += 1
 
     def load_state_dict(self, state_dict, strict=True):
@@ -185,22 +215,36 @@ class detector(torch.nn.Module):
 
     # ------------------------------------------------------------------ engine plumbing
     def engine_for(self, batch, h, w, **overrides):
+        """Engine for one input shape.  The cache is a small LRU (`max_cached_engines`, env DT_ENGINE_CACHE): the notebook flow over COCO meets
+        dozens of 32-aligned sizes and a workspace is ~1.5 GB at batch 1; the packed weights (0.5 GB) exist ONCE per model and are shared by
+        every engine (they do not depend on the shape), so building an engine for a new size costs descriptors + one workspace allocation."""
         key = (batch, h, w, tuple(sorted(overrides.items())))
         ent = self._engines.get(key)
-        if ent is None or ent[1] != self._weights_version:
-            dev = next(self.parameters()).device
-            if dev.type != 'cuda':
-                raise RuntimeError("detectorch_b200.detector runs on CUDA only: call model.cuda() first (no CPU fallback)")
-            kw = dict(arch=self.arch, batch=batch, height=h, width=w, num_classes=self.N_classes, use_mask=self.use_mask_head,
-                      output_prob=self.output_prob, emit_full_masks=True, det_cap=128, device=dev)
-            if self.family == "c4":
-                kw.update(model="c4", use_rpn=self.use_rpn_head, pre_nms_top_n=6000, post_nms_top_n=1000, exact_roialign=True)
-            kw.update(overrides)
+        if ent is not None and ent[1] == self._weights_version:
+            self._engines.move_to_end(key)
+            return ent[0]
+        dev = next(self.parameters()).device
+        if dev.type != 'cuda':
+            raise RuntimeError("detectorch_b200.detector runs on CUDA only: call model.cuda() first (no CPU fallback)")
+        kw = dict(arch=self.arch, batch=batch, height=h, width=w, num_classes=self.N_classes, use_mask=self.use_mask_head,
+                  output_prob=self.output_prob, emit_full_masks=True, det_cap=128, use_rpn=self.use_rpn_head, device=dev)
+        if self.family == "c4":
+            kw.update(model="c4", pre_nms_top_n=6000, post_nms_top_n=1000, exact_roialign=True)
+        kw.update(overrides)
+        for k in [k for k, v in self._engines.items() if v[1] != self._weights_version]:
+            del self._engines[k]                                    # stale weights
+        while len(self._engines) >= max(1, self.max_cached_engines):
+            self._engines.popitem(last=False)                       # least recently used
+        mk = tuple(sorted((k, str(v)) for k, v in kw.items() if k not in ("batch", "height", "width")))
+        donor = next((e for e, _ in self._engines.values() if getattr(e, "_mirror_model_key", None) == mk), None)
+        if donor is not None:
+            eng = Engine(share_weights_with=donor, **kw)
+        else:
             eng = Engine(**kw)
             eng.load_state_dict(self.state_dict())
-            ent = (eng, self._weights_version)
-            self._engines[key] = ent
-        return ent[0]
+        eng._mirror_model_key = mk
+        self._engines[key] = (eng, self._weights_version)
+        return eng
 
     def forward(self, image, rois=None, scaling_factor=None, roi_original_idx=None):
         """-> (cls_score [R,81], bbox_pred [R,324], rois [R,4], img_features [P2..P5])   detector.py:233-286.
@@ -210,18 +254,47 @@ class detector(torch.nn.Module):
         sf = float(scaling_factor.reshape(-1)[0]) if torch.is_tensor(scaling_factor) else float(1.0 if scaling_factor is None else scaling_factor)
         image = image.contiguous().float()
         if self.family == "fpn":
-            if rois is not None:
-                raise NotImplementedError("pre-computed proposals with the FPN body (eval_fast_FPN) are not built yet")
-            eng = self.engine_for(1, image.size(2), image.size(3))
-            self._activate(eng, sf)
-            eng.run(image, sf, ST_TRUNK, ST_BOX_HEAD)
-            n = int(eng.buffer("roi_counts")[0].item())
+            if self.use_rpn_head:
+                # the reference overwrites any `rois` argument with the RPN's proposals in this configuration (detector.py:241-257)
+                eng = self.engine_for(1, image.size(2), image.size(3))
+                eng.last_scaling_factor = sf
+                eng.run(image, sf, ST_TRUNK, ST_BOX_HEAD)
+                n = int(eng.buffer("roi_counts")[0].item())
+            else:
+                # Fast R-CNN on the FPN body (eval_fast_FPN.ipynb): rois = per-level list [rois_fpn2..5] (+ roi_original_idx), detector.py:263-270
+                if rois is None or not isinstance(rois, (list, tuple)):
+                    raise RuntimeError("Fast R-CNN with the FPN body needs the per-level proposal list [rois_fpn2, .., rois_fpn5] (eval_fast_FPN.ipynb)")
+                dev = image.device
+                parts, lv = [], []
+                for i, r in enumerate(rois):
+                    if r is None or r.numel() == 0:
+                        continue
+                    r = r.to(dev).float().reshape(-1, r.shape[-1])[:, -4:]          # preprocess_rois: [1,R,4] / [R,4] / [R,5]
+                    parts.append(r)
+                    lv.append(torch.full((r.size(0),), i, dtype=torch.int32, device=dev))
+                cat, lvl = torch.cat(parts, 0), torch.cat(lv, 0)
+                if roi_original_idx is not None:
+                    idx = roi_original_idx.to(dev).long().reshape(-1)
+                    cat, lvl = cat[idx], lvl[idx]
+                n = cat.size(0)
+                cap = min(1000, max(100, (n + 99) // 100 * 100))
+                if n > cap:
+                    raise RuntimeError("at most 1000 proposals per image are supported")
+                eng = self.engine_for(1, image.size(2), image.size(3), post_nms_top_n=cap)
+                eng.last_scaling_factor = sf
+                eng.run(image, sf, ST_TRUNK, ST_FPN)
+                er, el = eng.buffer("rois"), eng.buffer("roi_levels")
+                er.zero_(); el.zero_()
+                er[0, :n, 1:5] = cat
+                el[0, :n] = lvl
+                eng.buffer("roi_counts")[0] = n
+                eng.run(None, sf, ST_ROI_BOX, ST_BOX_HEAD)
             eng.check_range()
             feats = [eng.buffer("P%d" % l).permute(0, 3, 1, 2) for l in (2, 3, 4, 5)]     # NCHW-shaped views of the NHWC maps
         else:
             if self.use_rpn_head:
                 eng = self.engine_for(1, image.size(2), image.size(3))
-                self._activate(eng, sf)
+                eng.last_scaling_factor = sf
                 eng.run(image, sf, ST_TRUNK, ST_BOX_HEAD)
                 n = int(eng.buffer("roi_counts")[0].item())
                 eng.check_range()
@@ -234,7 +307,7 @@ class detector(torch.nn.Module):
                 if n > cap:
                     raise RuntimeError("at most 1000 proposals per image are supported")
                 eng = self.engine_for(1, image.size(2), image.size(3), post_nms_top_n=cap)
-                self._activate(eng, sf)
+                eng.last_scaling_factor = sf
                 eng.run(image, sf, ST_TRUNK, ST_TRUNK)
                 er = eng.buffer("rois")
                 er.zero_()
@@ -248,15 +321,11 @@ class detector(torch.nn.Module):
         out_rois = eng.buffer("rois")[0, :n, 1:5]
         return (cls_score, bbox_pred, out_rois, feats)
 
-    def _activate(self, eng, sf):
-        self._engine = eng
-        self._last_sf = sf
-        _result_utils.set_active_engine(eng)
-
     def _run_mask_head(self, img_features, rois, roi_original_idx):
-        eng = self._engine
+        # the engine is found from the feature maps it produced (no "current engine" state: two models / two image sizes may interleave)
+        eng = engine_owning(img_features)
         if eng is None:
-            raise RuntimeError("mask_head called before forward")
+            raise RuntimeError("mask_head: `img_features` must be the maps returned by this model's forward() (views of engine buffers)")
         if self.family == "c4":
             r = rois if torch.is_tensor(rois) else torch.cat(tuple(rois), 0)
             r = r.reshape(-1, r.shape[-1])[:, -4:].to(eng.device).float()        # detector.py:100-101 (preprocess_rois)
@@ -266,7 +335,7 @@ class detector(torch.nn.Module):
                 raise RuntimeError("mask_head: %d RoIs exceed the engine capacity %d" % (n, mr.size(0)))
             mr.zero_()
             mr[:n, 1:5] = r
-            eng.run(None, self._last_sf, ST_MASK_ROI_FEAT, ST_MASK_OUT)
+            eng.run(None, 1.0, ST_MASK_ROI_FEAT, ST_MASK_OUT)
             return eng.buffer("masks_full")[:n]
         # per-level lists -> original order (detector.py:103-106)
         lv, parts = [], []
@@ -289,7 +358,7 @@ class detector(torch.nn.Module):
         mr.zero_(); ml.zero_()
         mr[:n, 1:5] = cat
         ml[:n] = lvl
-        eng.run(None, self._last_sf, ST_MASK_ROI_FEAT, ST_MASK_OUT)
+        eng.run(None, 1.0, ST_MASK_ROI_FEAT, ST_MASK_OUT)
         return eng.buffer("masks_full")[:n]
 
     # ------------------------------------------------------------------ fused batched path
@@ -297,13 +366,13 @@ class detector(torch.nn.Module):
         """Fused path: images [B,3,H,W] -> dict of padded per-image detections (boxes [B,cap,4], scores, classes, counts,
         masks [B,cap,28,28] of the detected class).  No host synchronisation inside."""
         eng = self.engine_for(images.size(0), images.size(2), images.size(3))
-        self._engine = eng
-        self._last_sf = float(scaling_factor)
+        eng.last_scaling_factor = float(scaling_factor)
+        eng.set_original_size(0, 0)          # clip to the network input / scaling_factor (a previous postprocess_output may have set an image size)
         with_masks = self.use_mask_head if with_masks is None else with_masks
         eng.run(images.contiguous().float(), float(scaling_factor), ST_TRUNK, ST_MASK_OUT if with_masks else ST_DETECT)
         B, cap = images.size(0), eng.cfg.det_cap
         # "range_flag" (int32 [1]) is non-zero if an activation left the fp16 range of the default kind::f16 convolutions: read it together
-        # with the results (no extra synchronisation here), or call self._engine.check_range()
+        # with the results (no extra synchronisation here), or call engine_owning(out['boxes']).check_range()
         out = {"boxes": eng.buffer("det_boxes"), "scores": eng.buffer("det_scores"), "classes": eng.buffer("det_classes"),
                "counts": eng.buffer("det_counts"), "roi_idx": eng.buffer("det_roi_idx"), "range_flag": eng.buffer("range_flag")}
         if with_masks:

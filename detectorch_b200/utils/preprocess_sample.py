@@ -1,9 +1,11 @@
-"""Mirror of lib/utils/preprocess_sample.py:7-56 for the test-time image path (Faster / Mask R-CNN: no pre-computed proposals,
-or single-level pre-computed proposals): sample['image'] comes back as a CUDA FloatTensor [1,3,Hp,Wp] built on the device."""
+"""Mirror of lib/utils/preprocess_sample.py:7-56 for the test-time image path (Faster / Mask R-CNN: no proposals in the sample; Fast R-CNN:
+pre-computed proposals, single-level or distributed over the FPN levels): sample['image'] comes back as a CUDA FloatTensor [1,3,Hp,Wp]
+built on the device."""
 import numpy as np
 import torch
 
 from .blob import image_to_blob
+from .multilevel_rois import add_multilevel_rois_for_test
 
 
 class preprocess_sample(object):
@@ -27,12 +29,14 @@ class preprocess_sample(object):
         if 'dbentry' in sample:
             boxes = sample['dbentry']['boxes']
             if len(boxes) != 0:                                   # Fast R-CNN test: pre-computed proposals (preprocess_sample.py:37-47)
-                if self.fpn_on:
-                    raise NotImplementedError("pre-computed proposals with the FPN body (eval_fast_FPN) are not built")
                 proposals = boxes * scale
                 if self.remove_dup_proposals:
                     proposals, _ = self.remove_dup_prop(proposals)
-                sample['rois'] = torch.FloatTensor(proposals)
+                if not self.fpn_on:
+                    sample['rois'] = torch.FloatTensor(proposals)
+                else:                                              # rois, rois_fpn2..5, rois_idx_restore_int32 (preprocess_sample.py:43-46)
+                    for k, v in add_multilevel_rois_for_test({'rois': proposals}, 'rois').items():
+                        sample[k] = torch.FloatTensor(v)
             del sample['dbentry']
         return sample
 

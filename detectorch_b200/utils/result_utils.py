@@ -5,13 +5,28 @@ reference's numpy structures; and of segm_results (:170-228): mask paste + COCO 
 import numpy as np
 import torch
 
-from ..engine import ST_DETECT
-
-_active = {"engine": None}
+from ..engine import ST_DETECT, engine_owning
 
 
-def set_active_engine(engine):
-    _active["engine"] = engine
+def to_np(x):
+    """result_utils.py:25-30."""
+    if isinstance(x, np.ndarray):
+        return x
+    return x.detach().cpu().numpy()
+
+
+def empty_results(num_classes, num_images):
+    """result_utils.py:32-52: all_boxes[cls][image] = N x 5 array (x1, y1, x2, y2, score); all_segms[cls][image] = list of COCO RLE dicts in
+    1:1 correspondence; all_keyps likewise (unused by the detectors here).  Three independent nested lists (no shared inner lists)."""
+    def nest():
+        return [[[] for _ in range(num_images)] for _ in range(num_classes)]
+    return nest(), nest(), nest()
+
+
+def extend_results(index, all_res, im_res):
+    """result_utils.py:54-60: file one image's per-class results at `index`; class 0 (background) is skipped."""
+    for cls_idx in range(1, len(im_res)):
+        all_res[cls_idx][index] = im_res[cls_idx]
 
 
 def _as_float(x):
@@ -21,16 +36,23 @@ def _as_float(x):
 
 
 def postprocess_output(rois, scaling_factor, im_size, class_scores, bbox_deltas, bbox_reg_weights=(10.0, 10.0, 5.0, 5.0)):
-    """-> (scores_final [D], boxes_final [D,4], boxes_per_class list[81] of [n_j,5]) numpy, like result_utils.py:76-94."""
-    eng = _active["engine"]
+    """-> (scores_final [D], boxes_final [D,4], boxes_per_class list[81] of [n_j,5]) numpy, like result_utils.py:76-94.
+    The engine that runs the detection stage is the one whose buffers `class_scores` / `bbox_deltas` / `rois` are views of (what
+    detector.forward returned) -- there is no global "current engine", so several models / image sizes can be in flight."""
+    eng = engine_owning(class_scores, bbox_deltas, rois)
     if eng is None:
-        raise RuntimeError("postprocess_output: run detector.forward first (the engine owns the device buffers)")
+        raise RuntimeError("postprocess_output: class_scores / bbox_deltas must be the tensors returned by detector.forward "
+                           "(views of the engine's device buffers; clones or CPU copies carry no engine)")
     if tuple(bbox_reg_weights) != (10.0, 10.0, 5.0, 5.0):
         raise NotImplementedError("only the reference's default bbox_reg_weights are built")
     R = eng.cfg.post_nms_top_n
-    n = rois.shape[-2] if rois.dim() == 3 else rois.shape[0]
+    n = int(class_scores.shape[0])
+    nr = rois.shape[-2] if len(rois.shape) == 3 else rois.shape[0]
+    if nr != n:
+        raise RuntimeError("postprocess_output: %d rois for %d score rows" % (nr, n))
     if n > R:
         raise RuntimeError("postprocess_output: %d RoIs exceed the engine capacity %d" % (n, R))
+    rois = rois if torch.is_tensor(rois) else torch.as_tensor(np.asarray(rois))
     r = rois.reshape(-1, rois.shape[-1]).to(eng.device).float()
     er, ec, eb, en = eng.buffer("rois"), eng.buffer("cls_prob"), eng.buffer("bbox_pred"), eng.buffer("roi_counts")
     # inputs that already are the engine's own views are left in place; anything else is copied in

@@ -172,7 +172,8 @@ typedef struct dt_engine_config {
     int exact_roialign;          /* 1 = RoIAlign in the reference's exact fp32 operation order (bit-identical to its CPU loop);
                                     0 = separable / FMA fast path (fp32 re-association only, ~1e-7 relative) */
     int model_type;              /* 0 = R-50/101-FPN + RPN (+ '1up4convs' mask head); 1 = R-50/101-C4 (res5 head, 'upshare' mask head) */
-    int use_rpn;                 /* C4 only: 1 = Faster/Mask R-CNN (single-level RPN), 0 = Fast R-CNN (caller fills the `rois` buffer) */
+    int use_rpn;                 /* 1 = Faster/Mask R-CNN (RPN head + proposal generation on the device), 0 = Fast R-CNN with pre-computed
+                                    proposals (eval_fast.ipynb / eval_fast_FPN.ipynb): the caller fills `rois` (+ `roi_levels` for FPN), `roi_counts` */
     int conv_kind;               /* 0 = three-term product on the kind::f16 pipe (fp16 hi/lo halves, default: twice the tf32 issue rate; an
                                     activation >= 65504 raises the int32 buffer "range_flag"), 1 = 3xTF32 (no range limit) */
     int plane_handover;          /* kind::f16 only: 1 = conv1 of every bottleneck writes its output as two fp16 planes (hi, lo) that conv2 (3x3)
@@ -187,6 +188,9 @@ int64_t dt_engine_weight_bytes(dt_engine_t e);
 int64_t dt_engine_workspace_bytes(dt_engine_t e);
 /* attach caller-owned device memory and build the launch program (TMA descriptors) */
 int dt_engine_bind(dt_engine_t e, void* weights, void* workspace, dt_stream_t stream);
+/* same, on a weight buffer that another engine with the same model configuration (all of dt_engine_config but batch/height/width)
+ * has already loaded and finalised: packed weights are shape-independent, so engines for different image sizes share one copy */
+int dt_engine_attach(dt_engine_t e, void* loaded_weights, void* workspace, dt_stream_t stream);
 /* load one parameter by its reference state_dict name (torch layout, e.g. conv [Cout,Cin,kh,kw]); BN gains are
  * folded as g/sqrt(1+1e-5) (detector.py:231,301).  returns 1 loaded, 2 ignored (not on the hot path), 0 error */
 int dt_engine_load_param(dt_engine_t e, const char* name, const float* src_dev, int64_t numel, dt_stream_t stream);

@@ -1,7 +1,8 @@
-"""Overlay of the hot-path entries of lib/utils/result_utils.py (postprocess_output and segm_results on the device).  Everything
-else the notebooks import from utils.result_utils (empty_results, extend_results) still comes from the reference tree: append the
-reference's lib/ AFTER this overlay on sys.path and import those names from there."""
+"""Overlay of lib/utils/result_utils.py for notebooks that do `import utils.result_utils as result_utils` (eval_*.ipynb cell 1): every name
+the notebooks use -- empty_results (cell 9), postprocess_output / segm_results / extend_results (cell 10), to_np -- resolves to the B200
+mirror (postprocess_output and segm_results run on the device)."""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-from detectorch_b200.utils.result_utils import postprocess_output, segm_results  # noqa: E402,F401
+from detectorch_b200.utils.result_utils import (empty_results, extend_results, postprocess_output, segm_results,  # noqa: E402,F401
+                                                to_np)

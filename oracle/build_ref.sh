@@ -9,6 +9,11 @@
 #                                     (the reference CUDA kernel, compiled unmodified for sm_100a:
 #                                      the on-box "kernel to beat")
 #   _ref/cython_nms*.so           <- lib/utils_cython/cython_nms.pyx (patched as above)
+#   _ref/reflib.zip               <- the reference's pure-Python host modules (lib/utils, lib/data, lib/model), zipped unmodified:
+#                                     importable through zipimport, so that tests/test_gpu_notebooks.py can run the reference's OWN
+#                                     notebook cells (its collate_custom, to_cuda_variable, add_multilevel_rois_for_test ...) on the GPU
+#                                     box, where /root/reference does not exist
+#   _ref/notebook_cells.json      <- the code cells of the reference's eval_*.ipynb notebooks ({notebook: {cell index: source}})
 set -euo pipefail
 REF=${REF:-/root/reference}
 HERE=$(cd "$(dirname "$0")" && pwd)
@@ -32,4 +37,20 @@ setup(ext_modules=cythonize([Extension("cython_nms", ["cython_nms.pyx"], include
 PY
 (cd "$TMP" && python setup.py -q build_ext --inplace >/dev/null 2>&1 && cp cython_nms*.so "$OUT/")
 rm -rf "$TMP"
+python - "$REF" "$OUT" <<'PY'
+import json, os, sys, zipfile
+ref, out = sys.argv[1], sys.argv[2]
+with zipfile.ZipFile(os.path.join(out, "reflib.zip"), "w", zipfile.ZIP_DEFLATED) as z:
+    for pkg in ("utils", "data", "model"):
+        d = os.path.join(ref, "lib", pkg)
+        z.writestr(pkg + "/", "")          # explicit directory entry: zipimport then offers it as a namespace-package portion
+        for f in sorted(os.listdir(d)):
+            if f.endswith(".py"):
+                z.write(os.path.join(d, f), pkg + "/" + f)
+cells = {}
+for nb in sorted(f for f in os.listdir(ref) if f.startswith("eval_") and f.endswith(".ipynb")):
+    doc = json.load(open(os.path.join(ref, nb)))
+    cells[nb] = {str(i): "".join(c["source"]) for i, c in enumerate(doc["cells"]) if c["cell_type"] == "code"}
+json.dump(cells, open(os.path.join(out, "notebook_cells.json"), "w"))
+PY
 ls -la "$OUT"

@@ -291,12 +291,35 @@ def forward_fpn(image, P, arch="resnet50", scaling_factor=1.0, pre_nms=1000, pos
     return S
 
 
-def detect_and_mask_fpn(image, P, arch="resnet50", scaling_factor=1.0, **kw):
+def forward_fpn_precomputed(image, P, proposals, arch="resnet50", output_prob=True):
+    """detector.forward for Fast R-CNN on the FPN body (eval_fast_FPN.ipynb; detector.py:259-270 with `rois` a per-level list and
+    `roi_original_idx`): proposals [R,4] (network-input pixels) are distributed over P2..P5 by add_multilevel_rois_for_test
+    (preprocess_sample.py:43-46), pooled per level, concatenated and restored to the original order."""
+    assert image.size(0) == 1
+    S = {}
+    with torch.no_grad():
+        S["C"] = trunk(image, P, arch, 4)
+        S["P"] = fpn(S["C"], P)
+        pr = np.asarray(proposals, dtype=np.float32)
+        per_level, idx_restore = ref.multilevel_rois_for_test(pr)
+        feats = []
+        for i, r in enumerate(per_level):
+            feats.append(torch.from_numpy(ref.roi_align_forward(S["P"][i].numpy(), r, 7, 7, FPN_SCALES[i], 2)) if len(r) else torch.zeros((0, 256, 7, 7)))
+        idx = torch.as_tensor(idx_restore.astype(np.int64))
+        S["roi_feats"] = torch.cat(feats, 0)[idx]
+        S["rois"] = torch.from_numpy(np.concatenate(per_level, 0))[idx]
+        assert np.array_equal(S["rois"].numpy(), pr)
+        S["cls_score"], S["bbox_pred"], S["cls_logits"] = box_head_fpn(S["roi_feats"], P, output_prob)
+    return S
+
+
+def detect_and_mask_fpn(image, P, arch="resnet50", scaling_factor=1.0, im_size=None, **kw):
     """The full notebook step (eval_mask_FPN.ipynb cell 10): forward, postprocess_output,
-    re-split detections by level, mask head.  Returns the stage dict + detections + masks."""
+    re-split detections by level, mask head.  Returns the stage dict + detections + masks.
+    im_size: the ORIGINAL image (h, w) the boxes are clipped to (batch['original_im_size']); default: the blob size / scaling_factor."""
     S = forward_fpn(image, P, arch, scaling_factor, **kw)
     h, w = image.size(2), image.size(3)
-    im_size = np.array([h / scaling_factor, w / scaling_factor], dtype=np.float32)
+    im_size = np.array([h / scaling_factor, w / scaling_factor] if im_size is None else im_size[:2], dtype=np.float32)
     sf, bf, cb = ref.postprocess_output(S["rois"], scaling_factor, im_size, S["cls_score"], S["bbox_pred"])
     S["scores_final"], S["boxes_final"], S["cls_boxes"] = sf, bf, cb
     if len(bf):
@@ -357,10 +380,10 @@ def mask_head_c4(c4_feat, rois, P, arch="resnet50", output_prob=True):
     return (torch.sigmoid(logits) if output_prob else logits), logits, roi_feat
 
 
-def detect_and_mask_c4(image, P, arch="resnet50", proposals=None, scaling_factor=1.0, use_mask=True, **kw):
+def detect_and_mask_c4(image, P, arch="resnet50", proposals=None, scaling_factor=1.0, use_mask=True, im_size=None, **kw):
     S = forward_c4(image, P, arch, proposals, scaling_factor, **kw)
     h, w = image.size(2), image.size(3)
-    im_size = np.array([h / scaling_factor, w / scaling_factor], dtype=np.float32)
+    im_size = np.array([h / scaling_factor, w / scaling_factor] if im_size is None else im_size[:2], dtype=np.float32)
     sf, bf, cb = ref.postprocess_output(S["rois"], scaling_factor, im_size, S["cls_score"], S["bbox_pred"])
     S["scores_final"], S["boxes_final"], S["cls_boxes"] = sf, bf, cb
     if use_mask and len(bf):

@@ -34,6 +34,46 @@ def available():
     return os.path.isdir(os.path.join(REF, "lib")) and os.path.exists(os.path.join(_HERE, "_ref", "libroialign_ref.so"))
 
 
+def staged_available():
+    """oracle/_ref holds the reference's pure-Python host modules (reflib.zip) and its notebooks' code cells, staged by build_ref.sh where
+    the reference tree exists; unlike /root/reference these travel to the GPU box."""
+    return all(os.path.exists(os.path.join(_HERE, "_ref", f)) for f in ("reflib.zip", "notebook_cells.json")) and \
+        any(f.startswith("cython_nms") for f in os.listdir(os.path.join(_HERE, "_ref")))
+
+
+def install_compat(stub_plotting=False):
+    """Compat items 1, 2, 3 and 5 (no sys.path change): what ANY import of the reference's host modules needs under numpy 2 / python 3.12."""
+    for name, typ in (("float", float), ("int", int), ("bool", bool)):
+        if not hasattr(np, name):
+            setattr(np, name, typ)
+    if not hasattr(collections, "Mapping"):
+        collections.Mapping = collections.abc.Mapping
+        collections.Sequence = collections.abc.Sequence
+    stubs = ["pycocotools", "pycocotools.mask", "pycocotools.coco", "pycocotools.cocoeval"]
+    if stub_plotting:
+        stubs += ["matplotlib", "matplotlib.pyplot", "skimage", "skimage.io"]
+    for m in stubs:
+        if m not in sys.modules:
+            try:
+                __import__(m)
+            except Exception:
+                sys.modules[m] = types.ModuleType(m)
+                if "." in m:
+                    setattr(sys.modules[m.rsplit(".", 1)[0]], m.rsplit(".", 1)[1], sys.modules[m])
+    for m, attr in (("pycocotools.coco", "COCO"), ("pycocotools.cocoeval", "COCOeval")):      # `from pycocotools.coco import COCO` (json_dataset.py:37)
+        if not hasattr(sys.modules[m], attr):
+            setattr(sys.modules[m], attr, type(attr, (), {}))
+    if "utils_cython" not in sys.modules:
+        uc = types.ModuleType("utils_cython")
+        uc.__path__ = [os.path.join(_HERE, "_ref")]
+        sys.modules["utils_cython"] = uc
+        bb = types.ModuleType("utils_cython.cython_bbox")
+        bb.bbox_overlaps = None
+        sys.modules["utils_cython.cython_bbox"] = bb
+        import importlib
+        sys.modules["utils_cython.cython_nms"] = importlib.import_module("utils_cython.cython_nms")
+
+
 def install():
     """Make `import model.detector`, `import utils.boxes` ... resolve to the reference."""
     global _installed

@@ -131,3 +131,64 @@ def test_host_side_helpers():
         mult = ops.weight_multiplier(w_)
         assert 2.0 ** 13 <= m * mult < 2.0 ** 14 and np.log2(mult) == int(np.log2(mult))
     assert ops.weight_multiplier(torch.zeros(4)) == 1.0
+
+
+@pytest.mark.parametrize("notebook", ["eval_fast.ipynb", "eval_faster.ipynb", "eval_mask.ipynb", "eval_fast_FPN.ipynb", "eval_faster_FPN.ipynb",
+                                      "eval_mask_FPN.ipynb"])
+def test_notebook_setup_cells_run_on_the_overlay(built, tmp_path, notebook):
+    """CPU half of tests/test_gpu_notebooks.py: the reference notebook's import cell, paths cell, detector(...) constructor cell (with a
+    synthetic Detectron pickle -> load_pretrained_weights for that configuration) and the empty_results cell execute verbatim against the
+    lib/ overlay (the detection loop needs a GPU and runs in the gpu-marked test)."""
+    import pickle
+    import subprocess
+    import sys
+    from oracle import reference_shim as rs
+    if not rs.staged_available():
+        pytest.skip("oracle/_ref/reflib.zip not staged (oracle/build_ref.sh needs the reference tree once)")
+    out = os.path.join(str(tmp_path), "res.pkl")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "notebook_harness.py"), notebook, out, "--cpu"], capture_output=True, text=True,
+                       timeout=900, cwd=str(tmp_path))
+    assert r.returncode == 0 and "NOTEBOOK OK" in r.stdout, r.stderr[-3000:]
+    res = pickle.load(open(out, "rb"))
+    assert res["detector_module"] == "detectorch_b200.model.detector" and os.path.join(ROOT, "lib") in res["result_utils_file"]
+    assert len(res["all_boxes"]) == 81 and len(res["all_boxes"][1]) == 2 and res["all_boxes"][1][0] == []
+    assert res["all_boxes"][1] is not res["all_boxes"][2] and res["all_boxes"] is not res["all_segms"]
+
+
+def test_result_containers_and_multilevel_rois():
+    """empty_results / extend_results (result_utils.py:32-60) and the FPN level mapping used for pre-computed boxes
+    (multilevel_rois.py:19-82) -- host helpers of the mirror, against the oracle restatement."""
+    from detectorch_b200.utils import result_utils as ru
+    from detectorch_b200.utils.multilevel_rois import add_multilevel_rois_for_test
+    from oracle import ref
+    a, b, c = ru.empty_results(5, 3)
+    assert len(a) == 5 and all(len(x) == 3 for x in a) and a[1][0] == [] and a is not b and a[1] is not a[2] and a[1][0] is not a[1][1]
+    ru.extend_results(2, a, [["bg"], ["c1"], ["c2"], ["c3"], ["c4"]])
+    assert a[0][2] == [] and a[1][2] == ["c1"] and a[4][2] == ["c4"] and a[1][0] == []
+    rng = np.random.RandomState(3)
+    x1, y1 = rng.uniform(0, 900, 300), rng.uniform(0, 600, 300)
+    r = np.stack([x1, y1, x1 + np.exp(rng.uniform(1, 6.5, 300)), y1 + np.exp(rng.uniform(1, 6.5, 300))], 1).astype(np.float32)
+    blobs = add_multilevel_rois_for_test({'rois': r}, 'rois')
+    per_level, restore = ref.multilevel_rois_for_test(r)
+    for i, l in enumerate(range(2, 6)):
+        assert np.array_equal(blobs['rois_fpn%d' % l], per_level[i])
+    assert np.array_equal(blobs['rois_idx_restore_int32'], restore) and blobs['rois_idx_restore_int32'].dtype == np.int32
+    assert np.array_equal(np.concatenate(per_level, 0)[restore], r)
+
+
+def test_bn_running_stats_fold():
+    """Engine.load_state_dict folds non-trivial BatchNorm running statistics into the (gamma, beta) pair the engine applies as
+    gamma / sqrt(1 + eps), beta: the result must equal torch's eval-mode BatchNorm."""
+    from detectorch_b200.engine import fold_bn_running_stats
+    g = torch.Generator().manual_seed(0)
+    sd = {"model.bn1.weight": torch.rand(64, generator=g) + 0.5, "model.bn1.bias": torch.randn(64, generator=g),
+          "model.bn1.running_mean": torch.randn(64, generator=g), "model.bn1.running_var": torch.rand(64, generator=g) + 0.3,
+          "model.layer1.0.bn1.weight": torch.rand(8, generator=g), "model.layer1.0.bn1.bias": torch.randn(8, generator=g),
+          "model.layer1.0.bn1.running_mean": torch.zeros(8), "model.layer1.0.bn1.running_var": torch.ones(8)}
+    out = fold_bn_running_stats(sd)
+    x = torch.randn(2, 64, 5, 5, generator=g)
+    want = torch.nn.functional.batch_norm(x, sd["model.bn1.running_mean"], sd["model.bn1.running_var"], sd["model.bn1.weight"], sd["model.bn1.bias"],
+                                          False, 0.0, 1e-5)
+    got = x * (out["model.bn1.weight"] / np.sqrt(1 + 1e-5)).view(1, -1, 1, 1) + out["model.bn1.bias"].view(1, -1, 1, 1)
+    assert (got - want).abs().max().item() < 1e-5
+    assert out["model.layer1.0.bn1.weight"] is sd["model.layer1.0.bn1.weight"]      # trivial stats (the reference's case): untouched, bit-identical
