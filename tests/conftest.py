@@ -10,6 +10,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+    # the oracle (torch-CPU) runs on the threads this process may really use, not on every core of the machine
+    import torch
+    from oracle import usable_cpus
+    torch.set_num_threads(min(usable_cpus(), 64))
 
 
 @pytest.fixture(scope="session")
