@@ -172,10 +172,10 @@ class Engine:
         _live_engines.add(self)
 
     def model_key(self):
-        """Everything in the configuration that shapes the packed weight buffer / launch sequence -- all of it except batch, height, width."""
+        """What shapes the packed weight buffer (matrices, fp16 halves, and the per-conv-launch scale vectors, which are laid out in launch
+        order): the model and the numerics mode -- not the image size, RoI / detection capacities or thresholds."""
         c = self.cfg
-        skip = ("batch", "height", "width", "arch_blocks")
-        return tuple(c.arch_blocks) + tuple(getattr(c, f) for f, _ in c._fields_ if f not in skip)
+        return tuple(c.arch_blocks) + (c.num_classes, c.use_mask, c.model_type, c.use_rpn, c.conv_kind, c.precise_mask, c.passes, c.stem_im2col)
 
     def owns(self, ptr):
         return self._ws_lo <= ptr < self._ws_hi

@@ -156,6 +156,9 @@ class detector(torch.nn.Module):
         self.classif_head = torch.nn.Linear(feat, N_classes)
         if self.use_mask_head:
             self.mask_head = _MaskHead(self, output_prob, None if self.family == "fpn" else self.conv_head[0])
+        # Engine options of the mirror: full [D,81,M,M] masks are what model.mask_head returns (reference layout); a caller that only uses the
+        # fused detect() path may switch them off and size the padded detection slots (bench.py does)
+        self.engine_defaults = dict(emit_full_masks=True, det_cap=128)
         self._engines = collections.OrderedDict()      # LRU: (batch, h, w, overrides) -> (Engine, weights_version)
         self.max_cached_engines = int(os.environ.get("DT_ENGINE_CACHE", "6"))
         self._weights_version = 0
@@ -218,7 +221,7 @@ class detector(torch.nn.Module):
         """Engine for one input shape.  The cache is a small LRU (`max_cached_engines`, env DT_ENGINE_CACHE): the notebook flow over COCO meets
         dozens of 32-aligned sizes and a workspace is ~1.5 GB at batch 1; the packed weights (0.5 GB) exist ONCE per model and are shared by
         every engine (they do not depend on the shape), so building an engine for a new size costs descriptors + one workspace allocation."""
-        key = (batch, h, w, tuple(sorted(overrides.items())))
+        key = (batch, h, w, tuple(sorted(overrides.items())), tuple(sorted(self.engine_defaults.items())))
         ent = self._engines.get(key)
         if ent is not None and ent[1] == self._weights_version:
             self._engines.move_to_end(key)
@@ -227,7 +230,8 @@ class detector(torch.nn.Module):
         if dev.type != 'cuda':
             raise RuntimeError("detectorch_b200.detector runs on CUDA only: call model.cuda() first (no CPU fallback)")
         kw = dict(arch=self.arch, batch=batch, height=h, width=w, num_classes=self.N_classes, use_mask=self.use_mask_head,
-                  output_prob=self.output_prob, emit_full_masks=True, det_cap=128, use_rpn=self.use_rpn_head, device=dev)
+                  output_prob=self.output_prob, use_rpn=self.use_rpn_head, device=dev)
+        kw.update(self.engine_defaults)
         if self.family == "c4":
             kw.update(model="c4", pre_nms_top_n=6000, post_nms_top_n=1000, exact_roialign=True)
         kw.update(overrides)
@@ -235,7 +239,8 @@ class detector(torch.nn.Module):
             del self._engines[k]                                    # stale weights
         while len(self._engines) >= max(1, self.max_cached_engines):
             self._engines.popitem(last=False)                       # least recently used
-        mk = tuple(sorted((k, str(v)) for k, v in kw.items() if k not in ("batch", "height", "width")))
+        # what shapes the packed weight buffer (and the per-launch scale vectors in it): the model, not the image size / capacities
+        mk = tuple(sorted((k, str(v)) for k, v in kw.items() if k in ("arch", "num_classes", "use_mask", "model", "use_rpn", "conv_kind", "precise_mask", "passes")))
         donor = next((e for e, _ in self._engines.values() if getattr(e, "_mirror_model_key", None) == mk), None)
         if donor is not None:
             eng = Engine(share_weights_with=donor, **kw)
@@ -364,17 +369,49 @@ class detector(torch.nn.Module):
     # ------------------------------------------------------------------ fused batched path
     def detect(self, images, scaling_factor=1.0, with_masks=None):
         """Fused path: images [B,3,H,W] -> dict of padded per-image detections (boxes [B,cap,4], scores, classes, counts,
-        masks [B,cap,28,28] of the detected class).  No host synchronisation inside."""
+        masks [B,cap,28,28] of the detected class).  No host synchronisation inside.
+        `images` may live in (pinned) HOST memory: the upload then goes through two device staging buffers on a copy stream, so the
+        H2D copy of call i+1 overlaps the compute of call i.  The returned tensors are views of engine buffers: read them (e.g. an
+        asynchronous copy to pinned memory on the current stream) before the next detect() on the same input shape."""
+        if not self.use_rpn_head:
+            raise RuntimeError("detect() is the fused RPN path; Fast R-CNN configurations go through forward(image, rois)")
         eng = self.engine_for(images.size(0), images.size(2), images.size(3))
         eng.last_scaling_factor = float(scaling_factor)
         eng.set_original_size(0, 0)          # clip to the network input / scaling_factor (a previous postprocess_output may have set an image size)
         with_masks = self.use_mask_head if with_masks is None else with_masks
+        if not images.is_cuda:
+            images = self._upload(eng, images)
         eng.run(images.contiguous().float(), float(scaling_factor), ST_TRUNK, ST_MASK_OUT if with_masks else ST_DETECT)
+        st = getattr(eng, "_stage_state", None)
+        if st is not None and st["pending"] is not None:
+            st["free"][st["pending"]].record(torch.cuda.current_stream(eng.device))     # the staging buffer may be overwritten after this run
+            st["pending"] = None
         B, cap = images.size(0), eng.cfg.det_cap
         # "range_flag" (int32 [1]) is non-zero if an activation left the fp16 range of the default kind::f16 convolutions: read it together
         # with the results (no extra synchronisation here), or call engine_owning(out['boxes']).check_range()
         out = {"boxes": eng.buffer("det_boxes"), "scores": eng.buffer("det_scores"), "classes": eng.buffer("det_classes"),
                "counts": eng.buffer("det_counts"), "roi_idx": eng.buffer("det_roi_idx"), "range_flag": eng.buffer("range_flag")}
         if with_masks:
-            out["masks"] = eng.buffer("masks").view(B, cap, 28, 28)
+            m = eng.buffer("masks")
+            out["masks"] = m.view(B, cap, m.shape[-2], m.shape[-1])
         return out
+
+    def _upload(self, eng, host_images):
+        """Host -> device through two staging buffers and a dedicated copy stream (2-deep pipeline across successive detect() calls)."""
+        st = getattr(eng, "_stage_state", None)
+        if st is None:
+            with torch.cuda.device(eng.device):
+                st = {"buf": [torch.empty((eng.cfg.batch, 3, eng.cfg.height, eng.cfg.width), dtype=torch.float32, device=eng.device) for _ in range(2)],
+                      "up": [torch.cuda.Event() for _ in range(2)], "free": [torch.cuda.Event() for _ in range(2)],
+                      "stream": torch.cuda.Stream(device=eng.device), "i": 0, "pending": None}
+            eng._stage_state = st
+        b = st["i"] % 2
+        st["i"] += 1
+        cur = torch.cuda.current_stream(eng.device)
+        with torch.cuda.stream(st["stream"]):
+            st["stream"].wait_event(st["free"][b])              # no-op until the event has been recorded once
+            st["buf"][b].copy_(host_images, non_blocking=True)
+            st["up"][b].record(st["stream"])
+        cur.wait_event(st["up"][b])
+        st["pending"] = b
+        return st["buf"][b]

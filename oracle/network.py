@@ -19,6 +19,7 @@ torch / torchvision, which the reference does not vendor or pin; this file is pi
 against the reference's own modules executed by the torch in this image
 (tests/test_oracle.py::test_network_matches_reference, tests/golden/).
 """
+import time
 import zlib
 
 import numpy as np
@@ -138,6 +139,8 @@ def synthetic_params(arch="resnet50", fpn=True, rpn=True, mask=True, seed=0, n_c
         is_bn = (".bn" in name or "downsample.1" in name or name.startswith("model.bn1"))
         if is_bn and leaf == "weight":
             base = 0.35 if (name.endswith("bn3.weight")) else 1.0
+            if arch == "resnet101" and name.endswith("bn3.weight") and ".layer3." in name:
+                base = 0.18      # 23 residual additions instead of 6: keeps the R-101 maps at the R-50 scale (activations O(1-10), mask logits |x| < ~15)
             t = base * (0.8 + 0.4 * torch.rand(shape, generator=g))
         elif leaf == "bias":
             t = 0.1 * torch.randn(shape, generator=g)
@@ -258,18 +261,35 @@ def mask_head_fpn(feats, rois_per_level, idx_restore, P, output_prob=True, retur
     return out
 
 
-def forward_fpn(image, P, arch="resnet50", scaling_factor=1.0, pre_nms=1000, post_nms=1000, output_prob=True):
+class StageTimer:
+    """Wall-clock per stage of the CPU path (bench.py's per-stage break-out of the reference arm); a no-op when `timers` is None."""
+
+    def __init__(self, timers):
+        self.timers, self.t = timers, time.perf_counter()
+
+    def lap(self, name):
+        if self.timers is not None:
+            now = time.perf_counter()
+            self.timers[name] = self.timers.get(name, 0.0) + (now - self.t)
+            self.t = now
+
+
+def forward_fpn(image, P, arch="resnet50", scaling_factor=1.0, pre_nms=1000, post_nms=1000, output_prob=True, timers=None):
     """detector.forward for the FPN + RPN configuration, batch 1 (detector.py:233-286).
     Returns a dict of every teacher-forcing stage."""
     assert image.size(0) == 1
     h, w = image.size(2), image.size(3)
     S = {}
+    tm = StageTimer(timers)
     with torch.no_grad():
         S["C"] = trunk(image, P, arch, 4)
+        tm.lap("trunk")
         S["P"] = fpn(S["C"], P)
+        tm.lap("fpn")
         lv = S["P"] + [F.max_pool2d(S["P"][-1], 1, stride=2)]
         S["P6"] = lv[-1]
         S["rpn"] = [rpn_head(f, P) for f in lv]
+        tm.lap("rpn_head")
         scales = FPN_SCALES + [FPN_SCALES[-1] / 2.]
         S["props"] = []
         for i, (cls, box) in enumerate(S["rpn"]):
@@ -279,6 +299,7 @@ def forward_fpn(image, P, arch="resnet50", scaling_factor=1.0, pre_nms=1000, pos
         per_level, idx_restore, rois, lvls = ref.collect_and_distribute([p[0] for p in S["props"]],
                                                                         [p[1] for p in S["props"]], 2, 5, post_nms)
         S["rois_per_level"], S["idx_restore"], S["lvls"] = per_level, idx_restore, lvls
+        tm.lap("proposals_nms_collect")
         feats = []
         for i, r in enumerate(per_level):
             feats.append(torch.from_numpy(ref.roi_align_forward(S["P"][i].numpy(), r.numpy(), 7, 7, FPN_SCALES[i], 2))
@@ -287,7 +308,9 @@ def forward_fpn(image, P, arch="resnet50", scaling_factor=1.0, pre_nms=1000, pos
         S["rois"] = torch.cat(tuple(per_level), 0)[torch.as_tensor(idx_restore, dtype=torch.long)]
         assert torch.equal(S["rois"], rois)
         S["roi_feats"] = roi_feats
+        tm.lap("roialign_box")
         S["cls_score"], S["bbox_pred"], S["cls_logits"] = box_head_fpn(roi_feats, P, output_prob)
+        tm.lap("box_head")
     return S
 
 
@@ -318,16 +341,19 @@ def detect_and_mask_fpn(image, P, arch="resnet50", scaling_factor=1.0, im_size=N
     re-split detections by level, mask head.  Returns the stage dict + detections + masks.
     im_size: the ORIGINAL image (h, w) the boxes are clipped to (batch['original_im_size']); default: the blob size / scaling_factor."""
     S = forward_fpn(image, P, arch, scaling_factor, **kw)
+    tm = StageTimer(kw.get("timers"))
     h, w = image.size(2), image.size(3)
     im_size = np.array([h / scaling_factor, w / scaling_factor] if im_size is None else im_size[:2], dtype=np.float32)
     sf, bf, cb = ref.postprocess_output(S["rois"], scaling_factor, im_size, S["cls_score"], S["bbox_pred"])
     S["scores_final"], S["boxes_final"], S["cls_boxes"] = sf, bf, cb
+    tm.lap("postprocess_nms")
     if len(bf):
         per_level, idx = ref.multilevel_rois_for_test((bf * scaling_factor).astype(np.float32))
         S["mask_rois_per_level"], S["mask_idx_restore"] = per_level, idx
         with torch.no_grad():
             S["masks"], S["mask_logits"], S["mask_roi_feats"] = mask_head_fpn(S["P"], per_level, idx.astype(np.int64), P,
                                                                               True, return_logits=True)
+        tm.lap("mask_head")
     return S
 
 
@@ -341,14 +367,16 @@ def res5_head(x, P, arch="resnet50"):
     return F.adaptive_avg_pool2d(y, (1, 1)).view(y.size(0), -1), y
 
 
-def forward_c4(image, P, arch="resnet50", proposals=None, scaling_factor=1.0, pre_nms=6000, post_nms=1000, output_prob=True):
+def forward_c4(image, P, arch="resnet50", proposals=None, scaling_factor=1.0, pre_nms=6000, post_nms=1000, output_prob=True, timers=None):
     """detector.forward for the C4 configurations, batch 1 (detector.py:233-286): Fast R-CNN when `proposals` [R,4] is given
     (eval_fast.ipynb), Faster R-CNN otherwise (single-level RPN, eval_faster.ipynb)."""
     assert image.size(0) == 1
     h, w = image.size(2), image.size(3)
     S = {}
+    tm = StageTimer(timers)
     with torch.no_grad():
         S["C4"] = trunk(image, P, arch, 3)[-1]
+        tm.lap("trunk")
         if proposals is None:
             S["rpn"] = rpn_head(S["C4"], P)
             pr, sc, st = ref.generate_proposals_level(S["rpn"][0], S["rpn"][1], h, w, scaling_factor, 0.0625, C4_ANCHOR_SIZES,
@@ -358,14 +386,17 @@ def forward_c4(image, P, arch="resnet50", proposals=None, scaling_factor=1.0, pr
         else:
             rois = torch.as_tensor(proposals, dtype=torch.float32)
         S["rois"] = rois
+        tm.lap("rpn_proposals_nms")
         feats = torch.from_numpy(ref.roi_align_forward(S["C4"].numpy(), rois.numpy(), 14, 14, 0.0625, 0))
         S["roi_feats"] = feats
+        tm.lap("roialign_box")
         pooled, S["res5"] = res5_head(feats, P, arch)
         S["pooled"] = pooled
         cls = F.linear(pooled, P["classif_head.weight"], P["classif_head.bias"])
         S["cls_logits"] = cls
         S["cls_score"] = F.softmax(cls, dim=1) if output_prob else cls
         S["bbox_pred"] = F.linear(pooled, P["bbox_head.weight"], P["bbox_head.bias"])
+        tm.lap("res5_head")
     return S
 
 
@@ -382,10 +413,12 @@ def mask_head_c4(c4_feat, rois, P, arch="resnet50", output_prob=True):
 
 def detect_and_mask_c4(image, P, arch="resnet50", proposals=None, scaling_factor=1.0, use_mask=True, im_size=None, **kw):
     S = forward_c4(image, P, arch, proposals, scaling_factor, **kw)
+    tm = StageTimer(kw.get("timers"))
     h, w = image.size(2), image.size(3)
     im_size = np.array([h / scaling_factor, w / scaling_factor] if im_size is None else im_size[:2], dtype=np.float32)
     sf, bf, cb = ref.postprocess_output(S["rois"], scaling_factor, im_size, S["cls_score"], S["bbox_pred"])
     S["scores_final"], S["boxes_final"], S["cls_boxes"] = sf, bf, cb
+    tm.lap("postprocess_nms")
     if use_mask and len(bf):
         S["masks"], S["mask_logits"], S["mask_roi_feats"] = mask_head_c4(S["C4"], (bf * scaling_factor).astype(np.float32), P, arch)
     return S

@@ -15,8 +15,22 @@ import numpy as np
 import pytest
 import torch
 
+import os
+
 pytestmark = pytest.mark.gpu
 H, W = 800, 1216
+_REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "r02_parity_fullsize.txt")
+
+
+def report(line):
+    """Measured errors go to gpurun_out/ (copied to profiles/ as evidence); never fails a test."""
+    try:
+        os.makedirs(os.path.dirname(_REPORT), exist_ok=True)
+        with open(_REPORT, "a") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass
+    print(line)
 
 
 def _t(x):
@@ -113,13 +127,17 @@ def test_fpn_fullsize_activations(fpn_ctx):
     S, snap = fpn_ctx["S"], fpn_ctx["snap"]
     for b in range(2):
         for i in range(4):
-            assert rel_err(snap["C%d" % (i + 2)][b:b + 1].permute(0, 3, 1, 2), S[b]["C"][i]) < 1e-4, ("C", i + 2, b)
-            assert rel_err(snap["P%d" % (i + 2)][b:b + 1].permute(0, 3, 1, 2), S[b]["P"][i]) < 1e-4, ("P", i + 2, b)
+            ec = rel_err(snap["C%d" % (i + 2)][b:b + 1].permute(0, 3, 1, 2), S[b]["C"][i])
+            ep = rel_err(snap["P%d" % (i + 2)][b:b + 1].permute(0, 3, 1, 2), S[b]["P"][i])
+            report("R-50-FPN 800x1216 batch-2 image %d: C%d rel %.2e  P%d rel %.2e" % (b, i + 2, ec, i + 2, ep))
+            assert ec < 1e-4 and ep < 1e-4, ("C/P", i + 2, b)
         assert rel_err(snap["P6"][b:b + 1].permute(0, 3, 1, 2), S[b]["P6"]) < 1e-4
         for i in range(5):
             o = snap["rpn_out%d" % (i + 2)][b:b + 1]
-            assert abs_err(o[..., 0:3].permute(0, 3, 1, 2), S[b]["rpn"][i][0]) < 1e-4        # objectness probabilities
-            assert abs_err(o[..., 3:15].permute(0, 3, 1, 2), S[b]["rpn"][i][1]) < 1e-4       # box deltas
+            e0, e1 = abs_err(o[..., 0:3].permute(0, 3, 1, 2), S[b]["rpn"][i][0]), abs_err(o[..., 3:15].permute(0, 3, 1, 2), S[b]["rpn"][i][1])
+            report("R-50-FPN 800x1216 batch-2 image %d: RPN level P%d objectness abs %.2e  deltas abs %.2e" % (b, i + 2, e0, e1))
+            assert e0 < 1e-4        # objectness probabilities
+            assert e1 < 1e-4        # box deltas
 
 
 def test_fpn_fullsize_unforced_detections(fpn_ctx):
@@ -226,7 +244,7 @@ def test_fpn_fullsize_teacher_forced_mask_head(fpn_ctx):
         assert abs_err(mf, S[b]["mask_roi_feats"]) < 1e-5 * max(1.0, S[b]["mask_roi_feats"].abs().max().item())
         lg = eng.buffer("mask_logits")[b * cap:b * cap + D, :, :, :81].permute(0, 3, 1, 2)
         e = abs_err(lg, S[b]["mask_logits"])
-        print("image %d: mask logits abs err %.3e (|logit| max %.2f)" % (b, e, S[b]["mask_logits"].abs().max().item()))
+        report("R-50-FPN 800x1216 batch-2 image %d (teacher-forced): mask logits abs err %.3e (|logit| max %.2f)" % (b, e, S[b]["mask_logits"].abs().max().item()))
         assert e < 1e-4                                                                                   # north_star: 1e-4 on mask logits
         own = eng.buffer("masks")[b * cap:b * cap + D].cpu().numpy()
         assert np.abs(own - S[b]["masks"].numpy()[np.arange(D), want_cls]).max() < 1e-4
@@ -318,7 +336,9 @@ def test_r101_fullsize(built):
     eng.buffer("det_classes")[0, :D] = torch.from_numpy(want_cls.astype(np.int32)).to(dev)
     eng.run(None, 1.0, E.ST_MASK_ROIS, E.ST_MASK_OUT)
     torch.cuda.synchronize()
-    assert abs_err(eng.buffer("mask_logits")[:D, :, :, :81].permute(0, 3, 1, 2), S["mask_logits"]) < 1e-4
+    e = abs_err(eng.buffer("mask_logits")[:D, :, :, :81].permute(0, 3, 1, 2), S["mask_logits"])
+    report("R-101-FPN 800x1216 (teacher-forced): mask logits abs err %.3e (|logit| max %.2f)" % (e, S["mask_logits"].abs().max().item()))
+    assert e < 1e-4
 
 
 # ------------------------------------------------------------------------------------------ configs[4]: RoIAlign / NMS microbench sizes
