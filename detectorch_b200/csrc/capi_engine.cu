@@ -639,14 +639,18 @@ bool build_program(Engine* e, std::map<std::string, ConvW>* cw) {
             const int pl = c.plane_handover ? 1 : 0;
             pb.conv(ST_TRUNK, wp + "conv1", x, B, h, w, cin, e->buf(p + ".t1"), planes, 0, stride, true, RES_NONE, nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0,
                     0, 0, 0, false, 0, pl);
+            // conv2 -> conv3 the same way (plane_handover >= 2): conv3 is a 1x1 conv, so this saves one conversion per element, the converter
+            // warps' shared-memory round trip (16 KB read + 16 KB written per k-block) and their issue slots in the epilogue-bound conv3
+            const int pl2 = c.plane_handover >= 2 ? 1 : 0;
             pb.conv(ST_TRUNK, wp + "conv2", e->buf(p + ".t1"), B, ho, wo, planes, e->buf(p + ".t2"), planes, 1, 1, true, RES_NONE, nullptr, nullptr, 0, 0, 0,
-                    0, 0, 0, 0, 0, 0, 0, 0, 0, false, pl, 0);
+                    0, 0, 0, 0, 0, 0, 0, 0, 0, false, pl, pl2);
             const float* idt = x;
             if (b == 0) {
                 pb.conv(ST_TRUNK, wp + "downsample.0", x, B, h, w, cin, e->buf(p + ".ds"), planes * 4, 0, stride, false);
                 idt = e->buf(p + ".ds");
             }
-            pb.conv(ST_TRUNK, wp + "conv3", e->buf(p + ".t2"), B, ho, wo, planes, e->buf(p + ".out"), planes * 4, 0, 1, true, RES_TILE, idt);
+            pb.conv(ST_TRUNK, wp + "conv3", e->buf(p + ".t2"), B, ho, wo, planes, e->buf(p + ".out"), planes * 4, 0, 1, true, RES_TILE, idt, nullptr, 0, 0, 0,
+                    0, 0, 0, 0, 0, 0, 0, 0, 0, false, pl2, 0);
             x = e->buf(p + ".out");
             h = ho; w = wo; cin = planes * 4;
         }
