@@ -324,6 +324,14 @@ inline bool conv_build_stem(const float* x4, int B, int Hp, int Wp, int H1, int 
     return true;
 }
 
+// DT_CONV_PDL=1: conv launches carry the programmatic-stream-serialization attribute (see griddep_wait in common.cuh): the prologue of
+// launch i+1 overlaps the tail of launch i.  Only conv launches take part; every other kernel keeps plain stream order.
+inline bool conv_use_pdl() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DT_CONV_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 template <int BN, int NM, bool TWO, int KIND, int RING = 0>
 inline cudaError_t conv_launch_cfg(const ConvLayer& L, cudaStream_t stream) {
     using Cfg = ConvCfg<BN, NM, TWO, KIND, RING>;
@@ -332,6 +340,18 @@ inline cudaError_t conv_launch_cfg(const ConvLayer& L, cudaStream_t stream) {
         cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel<BN, NM, TWO, KIND, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
+    }
+    if (conv_use_pdl()) {
+        ConvParams prm = L.p;
+        prm.pdl = 1;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = L.grid; cfg.blockDim = dim3(Cfg::THREADS, 1, 1); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel<BN, NM, TWO, KIND, RING>, prm);
     }
     conv_tcgen05_kernel<BN, NM, TWO, KIND, RING><<<L.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(L.p);
     return cudaGetLastError();

@@ -90,6 +90,7 @@ struct ConvParams {
                            // operand tiles arrive by TMA and the converter warps have nothing to do
     int out_planes;        // KIND_F16X3: write the output as a pair of fp16 planes (hi = fp16(y), lo = fp16(y - hi)) instead of fp32
     int* range_flag;       // KIND_F16X3: set to 1 when an activation does not fit fp16 (|x| >= 65504 or NaN); may be null
+    int pdl;               // launched with programmatic stream serialization: release the next launch early, wait for the previous one
 };
 
 template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND, int RING = 0>
@@ -194,6 +195,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
     tc_fence_after();
     const uint32_t tmem_acc = *tmem_slot_gen;
     const uint32_t cta_rank = cluster_ctarank();
+    if (p.pdl) {
+        // Everything above (barrier init, TMEM allocation, descriptor prefetch, cluster handshake) touched no global data: with PDL it
+        // overlaps the tail of the previous launch on the SMs that launch has already left.  The next launch in the stream may become
+        // resident as soon as every CTA of this grid got here (it then parks in its own griddep_wait until this grid has completed).
+        griddep_launch_dependents();
+        griddep_wait();
+    }
 
     // work item -> tile coordinates.  The N-tile varies fastest so that consecutive items re-read the same A tile from L2.
     auto tile_of = [&](int item, int& w0, int& h0, int& n0img, int& n0) {
