@@ -4,7 +4,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdetectorch_b200.so")
+# DETECTORCH_B200_LIB selects another build of the same library (A/B experiments with compile-time kernel switches); default: the in-tree build
+LIB_PATH = os.environ.get("DETECTORCH_B200_LIB") or os.path.join(_HERE, "csrc", "libdetectorch_b200.so")
 _lib = None
 
 c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
@@ -31,6 +32,10 @@ SIGNATURES = {
                             c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dt_segm_paste": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                               c_void_p, c_void_p]),
+    "dt_roi_align_backward_det_workspace_bytes": (c_int64, [c_int64, c_int64]),
+    "dt_roi_align_backward_plan": (c_int, [c_void_p, c_int64, c_int, c_float, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "dt_roi_align_backward_deterministic": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
+                                                    c_int64, c_void_p, c_void_p, c_void_p]),
     "dt_prep_image": (c_int, [c_void_p, c_int, c_int, c_void_p, ctypes.c_double, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "dt_tf32_residual": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "dt_fp16_split": (c_int, [c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p]),

@@ -4,6 +4,7 @@
 #include "../../include/detectorch_b200.h"
 #include "conv_host.cuh"
 #include "roi_align.cuh"
+#include "roi_align_bwd.cuh"
 #include "segm.cuh"
 #include "sort_nms.cuh"
 
@@ -50,6 +51,74 @@ extern "C" int launch_roi_align_backward_cuda(const int nthreads, const float* t
     roi_align_backward_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(top_diff, bottom_rois, (long long)num_rois, roi_cols, channels, height,
                                                                           width, pooled_height, pooled_width, spatial_scale, sampling_ratio,
                                                                           bottom_diff);
+    DT_CHECK_CUDA(cudaGetLastError());
+    return 1;
+}
+
+// ---- deterministic backward (roi_align_bwd.cuh) ------------------------------------------------------------------------------------
+namespace {
+struct BwdWs { int* counts; long long* offsets; long long* total; uint32_t *k0, *k1; int *v0, *v1, *src; float *wgt, *cnt; };
+inline size_t bwd_align(size_t x) { return (x + 255) / 256 * 256; }
+inline BwdWs bwd_carve(void* ws, int64_t num_rois, int64_t total) {
+    uint8_t* p = reinterpret_cast<uint8_t*>(ws);
+    BwdWs w;
+    w.counts = reinterpret_cast<int*>(p); p += bwd_align((size_t)num_rois * 4);
+    w.offsets = reinterpret_cast<long long*>(p); p += bwd_align((size_t)(num_rois + 1) * 8);
+    w.total = reinterpret_cast<long long*>(p); p += 256;
+    const size_t m = bwd_align((size_t)total * 4);
+    w.k0 = reinterpret_cast<uint32_t*>(p); p += m; w.k1 = reinterpret_cast<uint32_t*>(p); p += m;
+    w.v0 = reinterpret_cast<int*>(p); p += m; w.v1 = reinterpret_cast<int*>(p); p += m;
+    w.src = reinterpret_cast<int*>(p); p += m; w.wgt = reinterpret_cast<float*>(p); p += m; w.cnt = reinterpret_cast<float*>(p);
+    return w;
+}
+}  // namespace
+
+extern "C" int64_t dt_roi_align_backward_det_workspace_bytes(int64_t num_rois, int64_t total_contributions) {
+    return (int64_t)(bwd_align((size_t)num_rois * 4) + bwd_align((size_t)(num_rois + 1) * 8) + 256 + 7 * bwd_align((size_t)total_contributions * 4));
+}
+
+// total number of (sample, corner) contributions of this RoI set = the size the workspace must provide; written to *total_dev (device int64).
+// scratch: device, >= dt_roi_align_backward_det_workspace_bytes(num_rois, 0) bytes.
+extern "C" int dt_roi_align_backward_plan(const float* rois, int64_t num_rois, int roi_cols, float spatial_scale, int pooled_height, int pooled_width,
+                                          int sampling_ratio, void* scratch, int64_t* total_dev, dt_stream_t stream) {
+    if (roi_cols != 4 && roi_cols != 5) { fprintf(stderr, "[detectorch_b200] roi_align backward: rois must have 4 or 5 columns\n"); return 0; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (num_rois <= 0) { DT_CHECK_CUDA(cudaMemsetAsync(total_dev, 0, 8, st)); return 1; }
+    BwdWs w = bwd_carve(scratch, num_rois, 0);
+    roi_bwd_count_kernel<<<(unsigned)((num_rois + 255) / 256), 256, 0, st>>>(rois, (int)num_rois, roi_cols, spatial_scale, pooled_height, pooled_width,
+                                                                            sampling_ratio, w.counts);
+    roi_bwd_scan_kernel<<<1, 1024, 0, st>>>(w.counts, (int)num_rois, w.offsets, reinterpret_cast<long long*>(total_dev));
+    DT_CHECK_CUDA(cudaGetLastError());
+    return 1;
+}
+
+// Deterministic, atomics-free twin of launch_roi_align_backward_cuda: bottom_diff [B,C,H,W] is accumulated into in exactly the order of the
+// reference CPU loop (lib/cppcuda/roi_align_backward_cpu.cpp:79-186) => bit-identical to it and bit-reproducible.  total_contributions is the
+// value dt_roi_align_backward_plan produced for these rois; workspace >= dt_roi_align_backward_det_workspace_bytes(num_rois, total).
+extern "C" int dt_roi_align_backward_deterministic(const float* top_diff, const float* rois, int64_t num_rois, int roi_cols, int batch, int channels,
+                                                   int height, int width, int pooled_height, int pooled_width, float spatial_scale,
+                                                   int sampling_ratio, int64_t total_contributions, float* bottom_diff, void* workspace,
+                                                   dt_stream_t stream) {
+    if (num_rois <= 0 || channels <= 0 || total_contributions <= 0) return 1;
+    if (roi_cols != 4 && roi_cols != 5) { fprintf(stderr, "[detectorch_b200] roi_align backward: rois must have 4 or 5 columns\n"); return 0; }
+    if (total_contributions >= (1ll << 31) || (int64_t)batch * height * width >= 0xffffffffll) {
+        fprintf(stderr, "[detectorch_b200] roi_align deterministic backward: problem too large for the 32-bit sort keys\n");
+        return 0;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    BwdWs w = bwd_carve(workspace, num_rois, total_contributions);
+    roi_bwd_count_kernel<<<(unsigned)((num_rois + 255) / 256), 256, 0, st>>>(rois, (int)num_rois, roi_cols, spatial_scale, pooled_height, pooled_width,
+                                                                            sampling_ratio, w.counts);
+    roi_bwd_scan_kernel<<<1, 1024, 0, st>>>(w.counts, (int)num_rois, w.offsets, w.total);
+    const long long bins = (long long)num_rois * pooled_height * pooled_width;
+    roi_bwd_emit_kernel<<<(unsigned)((bins + 255) / 256), 256, 0, st>>>(rois, (int)num_rois, roi_cols, spatial_scale, batch, height, width, pooled_height,
+                                                                       pooled_width, sampling_ratio, w.offsets, (long long)total_contributions, w.k0,
+                                                                       w.v0, w.src, w.wgt, w.cnt);
+    roi_bwd_sort_kernel<<<1, 1024, 0, st>>>(w.k0, w.v0, w.k1, w.v1, (int)total_contributions);
+    const long long cells = (long long)batch * height * width;
+    const int grid = (int)(cells < (long long)kNumSMs * 16 ? cells : (long long)kNumSMs * 16);
+    roi_bwd_reduce_kernel<<<grid, 256, 0, st>>>(w.k0, w.v0, (long long)total_contributions, w.src, w.wgt, w.cnt, top_diff, channels, height * width,
+                                               cells, pooled_height * pooled_width, bottom_diff);
     DT_CHECK_CUDA(cudaGetLastError());
     return 1;
 }

@@ -357,7 +357,10 @@ inline cudaError_t conv_launch_cfg(const ConvLayer& L, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-constexpr int kConvResRing = 3;
+#ifndef DT_CONV_RES_RING
+#define DT_CONV_RES_RING 3
+#endif
+constexpr int kConvResRing = DT_CONV_RES_RING;
 
 template <bool TWO, int KIND>
 inline cudaError_t conv_launch_sm(const ConvLayer& L, cudaStream_t stream) {

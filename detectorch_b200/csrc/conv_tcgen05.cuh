@@ -59,6 +59,9 @@ enum ConvKind { KIND_TF32X3 = 0, KIND_F16X3 = 1 };
 #ifndef DT_CONV_WARPS_NARROW
 #define DT_CONV_WARPS_NARROW 4
 #endif
+#ifndef DT_CONV_RING_SLOTS
+#define DT_CONV_RING_SLOTS 1       // epilogue staging slots per group in the residual-ring variant
+#endif
 
 struct ConvParams {
     CUtensorMap tm_a;      // 4D {C, W, H, N} over the NHWC input (elementStrides carry the conv stride)
@@ -107,7 +110,7 @@ struct ConvCfg {
     // epilogue staging: each of the two epilogue groups owns EPI_SLOTS 16 KB slots (128 rows x 32 channels).  Two slots per group let
     // the residual tile of the next chunk (RES_TILE) arrive, and the previous chunk's store drain, while the current chunk is computed;
     // they are taken whenever at least 3 pipeline stages still fit beside them.
-    static constexpr int EPI_SLOTS = (RING == 0 && (196608 - 2 * A_BYTES) / STAGE_BYTES >= 3) ? DT_CONV_EPI_SLOTS : 1;
+    static constexpr int EPI_SLOTS = RING > 0 ? DT_CONV_RING_SLOTS : (((196608 - 2 * A_BYTES) / STAGE_BYTES >= 3) ? DT_CONV_EPI_SLOTS : 1);
     // RING > 0 (short-K residual layers, where the epilogue IS the kernel): a ring of RING residual tiles per epilogue group is
     // prefetched by TMA RING chunks ahead, so the HBM latency of the residual never sits in the per-chunk chain; the mainloop
     // (<= 16 k-blocks per tile) makes do with two pipeline stages.

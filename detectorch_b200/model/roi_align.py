@@ -1,6 +1,8 @@
 """Drop-in mirror of the reference op wrapper lib/model/roi_align.py (RoIAlignFunction :23-145,
 RoIAlign :150-169, preprocess_rois :172-188) over the sm_100a kernel.  Same names, argument order
 and error behaviour; CUDA only (the reference's CPU branch is the parity oracle, not a product path)."""
+import os
+
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
@@ -27,11 +29,14 @@ class RoIAlignFunction(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output):
-        """Gradient w.r.t. the features (roi_align.py:91-147): zero-initialised [B,C,H,W], atomic scatter of the pooled gradient."""
+        """Gradient w.r.t. the features (roi_align.py:91-147): zero-initialised [B,C,H,W] that the pooled gradient is scattered into.
+        Default: the DETERMINISTIC kernel (every cell summed in the order of the reference's CPU backward: bit-identical to it, bit-reproducible
+        training steps).  DT_ROIALIGN_BACKWARD=atomic selects the reference GPU kernel's fp32 atomic scatter (faster, order-dependent last bits)."""
         if not grad_output.is_cuda:
             raise TypeError('detectorch_b200 RoIAlign runs on CUDA tensors only (no CPU fallback)')
-        grad_input = ops.roi_align_backward_nchw(ctx.rois.contiguous(), grad_output.contiguous().float(), tuple(ctx.features_size),
-                                                 int(ctx.pooled_height), int(ctx.pooled_width), float(ctx.spatial_scale), int(ctx.sampling_ratio))
+        fn = ops.roi_align_backward_nchw if os.environ.get("DT_ROIALIGN_BACKWARD", "deterministic") == "atomic" else ops.roi_align_backward_nchw_deterministic
+        grad_input = fn(ctx.rois.contiguous(), grad_output.contiguous().float(), tuple(ctx.features_size),
+                        int(ctx.pooled_height), int(ctx.pooled_width), float(ctx.spatial_scale), int(ctx.sampling_ratio))
         return grad_input, None, None, None, None, None
 
 

@@ -57,6 +57,35 @@ def roi_align_backward_nchw(rois, grad_output, features_size, pooled_height, poo
     return grad_input
 
 
+def roi_align_backward_nchw_deterministic(rois, grad_output, features_size, pooled_height, pooled_width, spatial_scale, sampling_ratio, grad_input=None):
+    """Same contract as roi_align_backward_nchw, without atomics: every feature-map cell sums its contributions in the order of the
+    reference's single-threaded CPU backward (lib/cppcuda/roi_align_backward_cpu.cpp:79-186), so the result is bit-identical to that loop
+    and bit-reproducible run to run.  One host read (the contribution count: the sampling grid is adaptive when sampling_ratio == 0)."""
+    _need_cuda(rois, grad_output)
+    B, C, H, W = [int(v) for v in features_size]
+    R = rois.size(0)
+    if grad_output.dim() != 4 or grad_output.size(0) != R or grad_output.size(1) != C:
+        raise RuntimeError("roi_align backward: grad_output must be [R,C,ph,pw]")
+    rois, grad_output = rois.contiguous().float(), grad_output.contiguous().float()
+    if grad_input is None:
+        grad_input = torch.zeros((B, C, H, W), device=grad_output.device, dtype=torch.float32)
+    if R == 0:
+        return grad_input
+    L = _lib.lib()
+    dev = grad_output.device
+    with torch.cuda.device(dev):
+        scratch = torch.empty((L.dt_roi_align_backward_det_workspace_bytes(R, 0),), dtype=torch.uint8, device=dev)
+        total = torch.zeros((1,), dtype=torch.int64, device=dev)
+        _lib.check(L.dt_roi_align_backward_plan(_p(rois), R, rois.size(1), float(spatial_scale), int(pooled_height), int(pooled_width),
+                                                int(sampling_ratio), _p(scratch), _p(total), _stream()), "dt_roi_align_backward_plan")
+        m = int(total.item())
+        ws = torch.empty((L.dt_roi_align_backward_det_workspace_bytes(R, m),), dtype=torch.uint8, device=dev)
+        _lib.check(L.dt_roi_align_backward_deterministic(_p(grad_output), _p(rois), R, rois.size(1), B, C, H, W, int(pooled_height), int(pooled_width),
+                                                         float(spatial_scale), int(sampling_ratio), m, _p(grad_input), _p(ws), _stream()),
+                   "dt_roi_align_backward_deterministic")
+    return grad_input
+
+
 def roi_align_forward_nchw_fast(features, rois, pooled_height, pooled_width, spatial_scale, sampling_ratio, out=None):
     """Same contract as roi_align_forward_nchw; sampling_ratio == 2 takes the separable / FMA fast path (fp32 re-association
     differences only), anything else is forwarded to the exact kernel."""

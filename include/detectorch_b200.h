@@ -44,6 +44,18 @@ int launch_roi_align_backward_cuda(const int nthreads, const float* top_diff, co
                                    const int pooled_width, const int sampling_ratio, float* bottom_diff, const float* bottom_rois,
                                    int roi_cols, dt_stream_t stream);
 
+/* Deterministic (atomics-free) backward: the contributions to every feature-map cell are summed in exactly the order of the reference's
+ * single-threaded CPU loop (lib/cppcuda/roi_align_backward_cpu.cpp:79-186) => bit-identical to it and bit-reproducible run to run
+ * (the atomic scatter above is neither).  Two calls: _plan writes the number of (sample, corner) contributions of the RoI set to *total_dev
+ * (device int64; the grid is adaptive when sampling_ratio == 0, so only the device knows it); the caller reads it, allocates
+ * dt_roi_align_backward_det_workspace_bytes(num_rois, total) bytes and calls _deterministic.  bottom_diff is accumulated into. */
+int64_t dt_roi_align_backward_det_workspace_bytes(int64_t num_rois, int64_t total_contributions);
+int dt_roi_align_backward_plan(const float* rois, int64_t num_rois, int roi_cols, float spatial_scale, int pooled_height, int pooled_width,
+                               int sampling_ratio, void* scratch, int64_t* total_dev, dt_stream_t stream);
+int dt_roi_align_backward_deterministic(const float* top_diff, const float* rois, int64_t num_rois, int roi_cols, int batch, int channels,
+                                        int height, int width, int pooled_height, int pooled_width, float spatial_scale, int sampling_ratio,
+                                        int64_t total_contributions, float* bottom_diff, void* workspace, dt_stream_t stream);
+
 /* 64-bit-safe variant (R*C*ph*pw may exceed 2^31, e.g. 100k RoIs x 256 ch x 14 x 14); roi_cols is 4 or 5
  * like the reference CPU loop (lib/cppcuda_cffi/src/cpp/roi_align_cpu_loop.h:5-17). */
 int dt_roi_align_forward_nchw(const float* features, const float* rois, int64_t num_rois, int roi_cols, int channels, int height,

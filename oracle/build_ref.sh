@@ -9,6 +9,10 @@
 #                                     (the reference CUDA kernel, compiled unmodified for sm_100a:
 #                                      the on-box "kernel to beat")
 #   _ref/cython_nms*.so           <- lib/utils_cython/cython_nms.pyx (patched as above)
+#   _ref/libroialign_bwd_ref.so   <- lib/cppcuda/roi_align_backward_cpu.cpp: the file is ATen-0.4 flavoured and does not compile against
+#                                     torch 2.x, but its templates bilinear_interpolate_gradient / add / roi_align_backward_loop
+#                                     (from the first "template" line to the "} // ROIAlignBackward" line) are plain C++: exactly those lines
+#                                     are cut out by sed into a temp file and instantiated for float behind an extern "C" entry point
 #   _ref/reflib.zip               <- the reference's pure-Python host modules (lib/utils, lib/data, lib/model), zipped unmodified:
 #                                     importable through zipimport, so that tests/test_gpu_notebooks.py can run the reference's OWN
 #                                     notebook cells (its collate_custom, to_cuda_variable, add_multilevel_rois_for_test ...) on the GPU
@@ -25,6 +29,16 @@ if command -v nvcc >/dev/null; then
   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -shared \
        -o "$OUT/libroialign_ref_cuda.so" "$REF/lib/cppcuda_cffi/src/cuda/roi_align_forward_cuda_kernel.cu"
 fi
+TMPB=$(mktemp -d)
+{ echo '#include <algorithm>'; echo '#include <cmath>'; echo 'namespace refbwd {';
+  sed -n '/^template <typename T>/,/^} \/\/ ROIAlignBackward/p' "$REF/lib/cppcuda/roi_align_backward_cpu.cpp";
+  echo '}';
+  echo 'extern "C" void roi_align_backward_loop_f32(int nthreads, const float* top_diff, int num_rois, float spatial_scale, int channels, int height,';
+  echo '    int width, int pooled_height, int pooled_width, int sampling_ratio, float* bottom_diff, const float* bottom_rois, int rois_cols) {';
+  echo '  refbwd::roi_align_backward_loop<float>(nthreads, top_diff, num_rois, spatial_scale, channels, height, width, pooled_height, pooled_width,';
+  echo '                                         sampling_ratio, bottom_diff, bottom_rois, rois_cols); }'; } > "$TMPB/bwd.cpp"
+g++ -O2 -fPIC -shared -o "$OUT/libroialign_bwd_ref.so" "$TMPB/bwd.cpp"
+rm -rf "$TMPB"
 TMP=$(mktemp -d)
 sed -e 's/np\.int_t/np.intp_t/g' -e 's/dtype=np\.int)/dtype=np.intp)/g' \
     "$REF/lib/utils_cython/cython_nms.pyx" > "$TMP/cython_nms.pyx"

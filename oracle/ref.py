@@ -90,6 +90,32 @@ def roi_align_forward_ref(features, rois, pooled_h, pooled_w, spatial_scale, sam
     return out
 
 
+def roi_align_backward(top_diff, rois, features_shape, pooled_h, pooled_w, spatial_scale, sampling_ratio):
+    """top_diff [R,C,ph,pw] fp32, rois [R,4|5] -> gradient w.r.t. the features [B,C,H,W] (numpy), the order of additions into every
+    cell being that of the reference's single-threaded CPU loop (lib/cppcuda/roi_align_backward_cpu.cpp:79-186)."""
+    t = np.ascontiguousarray(np.asarray(top_diff, dtype=np.float32))
+    r = np.ascontiguousarray(np.asarray(rois, dtype=np.float32))
+    B, C, H, W = [int(v) for v in features_shape]
+    out = np.zeros((B, C, H, W), np.float32)
+    lib().oracle_roi_align_backward(_fp(t), _fp(r), ctypes.c_int64(r.shape[0]), ctypes.c_int(r.shape[1]), ctypes.c_int(C), ctypes.c_int(H),
+                                    ctypes.c_int(W), ctypes.c_int(pooled_h), ctypes.c_int(pooled_w), ctypes.c_float(spatial_scale),
+                                    ctypes.c_int(sampling_ratio), _fp(out))
+    return out
+
+
+def roi_align_backward_ref(top_diff, rois, features_shape, pooled_h, pooled_w, spatial_scale, sampling_ratio):
+    """Same through the reference's own loop template (oracle/_ref/libroialign_bwd_ref.so, cut out of roi_align_backward_cpu.cpp by build_ref.sh)."""
+    so = ctypes.CDLL(os.path.join(_HERE, "_ref", "libroialign_bwd_ref.so"))
+    t = np.ascontiguousarray(np.asarray(top_diff, dtype=np.float32))
+    r = np.ascontiguousarray(np.asarray(rois, dtype=np.float32))
+    B, C, H, W = [int(v) for v in features_shape]
+    out = np.zeros((B, C, H, W), np.float32)
+    so.roi_align_backward_loop_f32(ctypes.c_int(t.size), _fp(t), ctypes.c_int(r.shape[0]), ctypes.c_float(spatial_scale), ctypes.c_int(C), ctypes.c_int(H),
+                                   ctypes.c_int(W), ctypes.c_int(pooled_h), ctypes.c_int(pooled_w), ctypes.c_int(sampling_ratio), _fp(out), _fp(r),
+                                   ctypes.c_int(r.shape[1]))
+    return out
+
+
 # ----------------------------------------------------------------------------- NMS
 def nms(dets, thresh):
     """dets [N,5] fp32 (x1,y1,x2,y2,score) -> ascending original indices kept (int64).

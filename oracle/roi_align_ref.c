@@ -90,3 +90,54 @@ void oracle_roi_align_forward(const float* features, const float* rois, int64_t 
         free(taps);
     }
 }
+
+/*
+ * RoIAlign BACKWARD (gradient w.r.t. the features) -- restatement of the reference's single-threaded CPU loop
+ *   lib/cppcuda/roi_align_backward_cpu.cpp:79-186 (loop), :10-71 (bilinear_interpolate_gradient),
+ * the training-side twin of the forward above.  bottom_diff [B,C,H,W] is ACCUMULATED into.
+ * The reference visits the pooled elements in (n, c, ph, pw) order and adds g_k = top * w_k / count to the 4 corner cells of every
+ * sample; what fixes the fp32 result is, per (cell, channel), the ORDER of those additions: (n, ph, pw, iy, ix, corner 1..4).
+ * Written independently (the taps of a bin are computed once and shared by all channels, loop order n, ph, pw, c) with that per-cell
+ * order preserved, so the result is bit-identical.  Pinned against the reference's own loop compiled into oracle/_ref/
+ * (libroialign_bwd_ref.so, build_ref.sh) in tests/test_oracle.py.
+ */
+void oracle_roi_align_backward(const float* top_diff, const float* rois, int64_t R, int roi_cols,
+                               int C, int H, int W, int PH, int PW,
+                               float spatial_scale, int sampling_ratio, float* bottom_diff)
+{
+    for (int64_t n = 0; n < R; ++n) {
+        const float* r = rois + n * roi_cols;
+        int b = 0;
+        if (roi_cols == 5) { b = (int)r[0]; ++r; }                       /* :104-108 */
+        float sw = r[0] * spatial_scale, sh = r[1] * spatial_scale;       /* :111-114 */
+        float ew = r[2] * spatial_scale, eh = r[3] * spatial_scale;
+        float rw = fmaxf(ew - sw, 1.f), rh = fmaxf(eh - sh, 1.f);         /* :121-122 */
+        float bh = rh / (float)PH, bw = rw / (float)PW;
+        int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rh / PH);   /* :134-138 */
+        int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rw / PW);
+        const float count = (float)(gh * gw);                             /* :141 */
+        tap4_t* taps = (tap4_t*)malloc(sizeof(tap4_t) * (size_t)gh * gw);
+        unsigned char* ok = (unsigned char*)malloc((size_t)gh * gw);
+        for (int ph = 0; ph < PH; ++ph)
+        for (int pw = 0; pw < PW; ++pw) {
+            for (int iy = 0; iy < gh; ++iy) {
+                const float y = sh + ph * bh + (float)(iy + .5f) * bh / (float)gh;      /* :144-146 */
+                for (int ix = 0; ix < gw; ++ix) {
+                    const float x = sw + pw * bw + (float)(ix + .5f) * bw / (float)gw;  /* :148-150 */
+                    sample_taps(y, x, H, W, &taps[iy * gw + ix]);         /* same clamps / weights as :10-71 */
+                    ok[iy * gw + ix] = !(y < -1.0 || y > H || x < -1.0 || x > W);       /* :26-31: all indices -1 -> no add (:168) */
+                }
+            }
+            for (int c = 0; c < C; ++c) {
+                float* plane = bottom_diff + ((int64_t)b * C + c) * H * W;
+                const float top = top_diff[((n * C + c) * PH + ph) * PW + pw];
+                for (int s = 0; s < gh * gw; ++s) {
+                    if (!ok[s]) continue;
+                    const tap4_t* t = &taps[s];
+                    for (int k = 0; k < 4; ++k) plane[t->p[k]] += top * t->w[k] / count;   /* :163-173, g1..g4 in order */
+                }
+            }
+        }
+        free(taps); free(ok);
+    }
+}
