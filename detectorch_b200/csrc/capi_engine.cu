@@ -394,6 +394,7 @@ void plan_buffers(Engine* e) {
         add_buf(e, "rpn_v0", {B, anchors_total}, 1); add_buf(e, "rpn_v1", {B, anchors_total}, 1);
         add_buf(e, "rpn_cand", {B, L, pre, 4}); add_buf(e, "rpn_cand_score", {B, L, pre});
         add_buf(e, "rpn_order", {B, L, pre}, 1);
+        add_buf(e, "rpn_sel_hist", {B, L, 2, 2048}, 1); add_buf(e, "rpn_sel_cc", {B, L, kRpnMaxChunks}, 1); add_buf(e, "rpn_sel_info", {B, L, 4}, 1);
         add_buf(e, "props", {B, L, post, 4}); add_buf(e, "prop_scores", {B, L, post}); add_buf(e, "prop_counts", {B, L}, 1);
         add_buf(e, "col_k0", {B, L * post}, 1); add_buf(e, "col_k1", {B, L * post}, 1);
         add_buf(e, "col_v0", {B, L * post}, 1); add_buf(e, "col_v1", {B, L * post}, 1);
@@ -517,11 +518,30 @@ cudaError_t fn_p6(Engine* e, cudaStream_t s) {
     subsample2_nhwc_kernel<<<grid_for(n), 256, 0, s>>>(e->buf("P5"), e->cfg.batch, e->LH[3], e->LW[3], 256, e->LH[4], e->LW[4], e->buf("P6"));
     return cudaGetLastError();
 }
-cudaError_t fn_proposals(Engine* e, cudaStream_t s) {
-    e->rpn.scaling_factor = e->scaling_factor;
-    rpn_proposals_kernel<<<dim3(5, e->cfg.batch), 1024, 0, s>>>(e->rpn);
+// Proposal generation: the keys / two-level radix select / ordered compaction of every (level, image) run at full-GPU width
+// (rpn_select_*_kernel, one CTA per 4096 anchors), then one CTA per (level, image) sorts the ~1000 selected candidates, decodes, clips,
+// filters and runs the NMS.  DT_RPN_SPLIT=0 keeps the whole level in that one CTA (the round-1 kernel; P2's 182 400 anchors were its long pole).
+cudaError_t launch_proposals(Engine* e, cudaStream_t s, int levels) {
+    static int split = -1;
+    if (split < 0) { const char* v = getenv("DT_RPN_SPLIT"); split = (v && v[0] == '0') ? 0 : 1; }
+    RpnParams& P = e->rpn;
+    P.scaling_factor = e->scaling_factor;
+    int max_n = 0;
+    for (int l = 0; l < levels; ++l) max_n = std::max(max_n, P.lv[l].n);
+    P.split = (split && max_n <= kRpnChunk * kRpnMaxChunks) ? 1 : 0;
+    if (P.split) {
+        cudaError_t err = cudaMemsetAsync(P.sel_hist, 0, (size_t)e->cfg.batch * levels * 4096 * sizeof(uint32_t), s);
+        if (err != cudaSuccess) return err;
+        const dim3 grid((max_n + kRpnChunk - 1) / kRpnChunk, levels, e->cfg.batch);
+        rpn_select_keys_kernel<<<grid, 1024, 0, s>>>(P);
+        rpn_select_hist2_kernel<<<grid, 1024, 0, s>>>(P);
+        rpn_select_count_kernel<<<grid, 1024, 0, s>>>(P);
+        rpn_select_scatter_kernel<<<grid, 1024, 0, s>>>(P);
+    }
+    rpn_proposals_kernel<<<dim3(levels, e->cfg.batch), 1024, 0, s>>>(P);
     return cudaGetLastError();
 }
+cudaError_t fn_proposals(Engine* e, cudaStream_t s) { return launch_proposals(e, s, 5); }
 cudaError_t fn_collect(Engine* e, cudaStream_t s) {
     collect_kernel<<<e->cfg.batch, 1024, 0, s>>>(e->col);
     return cudaGetLastError();
@@ -703,6 +723,7 @@ bool build_program(Engine* e, std::map<std::string, ConvW>* cw) {
         P.cand = e->buf<float4>("rpn_cand"); P.cand_score = e->buf("rpn_cand_score");
         P.out_props = e->buf("props"); P.out_scores = e->buf("prop_scores"); P.out_counts = e->buf<int>("prop_counts");
         P.dbg_order = e->buf<int>("rpn_order");
+        P.sel_hist = e->buf<uint32_t>("rpn_sel_hist"); P.sel_chunk_counts = e->buf<int>("rpn_sel_cc"); P.sel_info = e->buf<int>("rpn_sel_info");
         pb.fn(ST_PROPOSALS, fn_proposals);
         CollectParams& C = e->col;
         memset(&C, 0, sizeof(C));
@@ -1014,7 +1035,8 @@ int dt_engine_count_launches(dt_engine_t h, int first_stage, int last_stage) {
     Engine* e = reinterpret_cast<Engine*>(h);
     int n = 0;
     for (const Op& op : e->ops)
-        if (op.stage >= first_stage && op.stage <= last_stage) n += (op.kind == 1 && e->fns[op.fn] == fn_detect) ? 2 : 1;
+        if (op.stage >= first_stage && op.stage <= last_stage)
+            n += (op.kind == 1 && e->fns[op.fn] == fn_detect) ? 2 : ((op.kind == 1 && op.stage == ST_PROPOSALS) ? (e->rpn.split ? 5 : 1) : 1);
     return n;
 }
 

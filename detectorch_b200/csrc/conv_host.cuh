@@ -113,6 +113,7 @@ struct ConvLayer {
     bool two_sm = true; // cta_group::2 MMA (default) vs 1-SM MMA + multicast (DT_CONV_1SM=1)
     int kind = KIND_TF32X3;
     int ring = 0;       // residual prefetch ring (short-K RES_TILE layers)
+    int slots = 1;      // epilogue staging slots per group (2 = the TMA store of a chunk drains while the next chunk is computed)
     dim3 grid;
     bool valid = false;
 };
@@ -282,6 +283,18 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
         // stages are too few for 16 k-blocks per tile)
         L->ring = (use_ring && L->nmain == 0 && L->two_sm && L->kind == KIND_F16X3 && s.res_mode == RES_TILE && p.ntaps * p.cin_blocks <= 8) ? 1 : 0;
     }
+    {
+        // Two staging slots per epilogue group wherever they do not cost a pipeline stage that the layer needs: every tile up to 128 wide
+        // (their stages are 40 KB: four still fit), and the 256-wide layers with at most 8 k-blocks per tile (K <= 256), whose time is the
+        // epilogue.  Long-K 256-wide layers keep one slot and four stages.  The residual-ring variant then runs ring 2 + slots 2 instead
+        // of ring 3 + slot 1 (-10 % on the conv3 + residual layers).  DT_CONV_SLOTS=1|2 forces one setting (A/B, tests).
+        static int force = -1;
+        if (force < 0) { const char* e = getenv("DT_CONV_SLOTS"); force = e ? atoi(e) : 0; }
+        const int kb = p.ntaps * p.cin_blocks;
+        L->slots = (bn <= 128 || (bn == 256 && L->nmain == 0 && kb <= 8)) ? 2 : 1;
+        if (force == 1) L->slots = 1;
+        if (force == 2 && !(bn == 256 && L->nmain != 0)) L->slots = 2;
+    }
     return true;
 }
 
@@ -320,6 +333,7 @@ inline bool conv_build_stem(const float* x4, int B, int Hp, int Wp, int H1, int 
     p.a_tile_bytes = wbox * hbox * nbox * 128;
     p.relu = 1; p.sigmoid_ch = 0; p.res_mode = RES_NONE; p.passes = passes == 1 ? 1 : 3;
     L->nmain = 3;
+    L->slots = 2;
     finish_grid(L, 1);
     return true;
 }
@@ -332,12 +346,12 @@ inline bool conv_use_pdl() {
     return v == 1;
 }
 
-template <int BN, int NM, bool TWO, int KIND, int RING = 0>
+template <int BN, int NM, bool TWO, int KIND, int RING = 0, int SLOTS = 1>
 inline cudaError_t conv_launch_cfg(const ConvLayer& L, cudaStream_t stream) {
-    using Cfg = ConvCfg<BN, NM, TWO, KIND, RING>;
+    using Cfg = ConvCfg<BN, NM, TWO, KIND, RING, SLOTS>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel<BN, NM, TWO, KIND, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel<BN, NM, TWO, KIND, RING, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -351,26 +365,33 @@ inline cudaError_t conv_launch_cfg(const ConvLayer& L, cudaStream_t stream) {
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel<BN, NM, TWO, KIND, RING>, prm);
+        return cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel<BN, NM, TWO, KIND, RING, SLOTS>, prm);
     }
-    conv_tcgen05_kernel<BN, NM, TWO, KIND, RING><<<L.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(L.p);
+    conv_tcgen05_kernel<BN, NM, TWO, KIND, RING, SLOTS><<<L.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(L.p);
     return cudaGetLastError();
 }
 
-#ifndef DT_CONV_RES_RING
-#define DT_CONV_RES_RING 3
-#endif
-constexpr int kConvResRing = DT_CONV_RES_RING;
+// residual prefetch ring depth of the short-K residual layers: 3 tiles with one staging slot per group, 2 tiles with two slots
+constexpr int kConvResRing1 = 3, kConvResRing2 = 2;
 
 template <bool TWO, int KIND>
 inline cudaError_t conv_launch_sm(const ConvLayer& L, cudaStream_t stream) {
+    // two staging slots only in the kind::f16 kernels (the engine default): the tf32 kind's stages are twice as large
+    constexpr bool kCan2 = KIND == KIND_F16X3;
+    const bool s2 = kCan2 && L.slots == 2;
+    constexpr int S2 = kCan2 ? 2 : 1;
     switch (L.block_n) {
-        case 64: return conv_launch_cfg<64, 3, TWO, KIND>(L, stream);
-        case 128: return L.nmain == 3 ? conv_launch_cfg<128, 3, TWO, KIND>(L, stream) : conv_launch_cfg<128, 1, TWO, KIND>(L, stream);
+        case 64: return s2 ? conv_launch_cfg<64, 3, TWO, KIND, 0, S2>(L, stream) : conv_launch_cfg<64, 3, TWO, KIND, 0, 1>(L, stream);
+        case 128:
+            if (L.nmain == 3) return s2 ? conv_launch_cfg<128, 3, TWO, KIND, 0, S2>(L, stream) : conv_launch_cfg<128, 3, TWO, KIND, 0, 1>(L, stream);
+            return s2 ? conv_launch_cfg<128, 1, TWO, KIND, 0, S2>(L, stream) : conv_launch_cfg<128, 1, TWO, KIND, 0, 1>(L, stream);
         case 256:
             if (L.nmain == 0) {
-                if constexpr (TWO && KIND == KIND_F16X3) { if (L.ring) return conv_launch_cfg<256, 0, TWO, KIND, kConvResRing>(L, stream); }
-                return conv_launch_cfg<256, 0, TWO, KIND>(L, stream);
+                if constexpr (TWO && KIND == KIND_F16X3) {
+                    if (L.ring) return s2 ? conv_launch_cfg<256, 0, TWO, KIND, kConvResRing2, 2>(L, stream) : conv_launch_cfg<256, 0, TWO, KIND, kConvResRing1, 1>(L, stream);
+                }
+                if constexpr (TWO && KIND == KIND_F16X3) { if (s2) return conv_launch_cfg<256, 0, TWO, KIND, 0, 2>(L, stream); }
+                return conv_launch_cfg<256, 0, TWO, KIND, 0, 1>(L, stream);
             }
             return conv_launch_cfg<256, 1, TWO, KIND>(L, stream);
         default: return cudaErrorInvalidValue;

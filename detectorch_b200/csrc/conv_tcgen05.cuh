@@ -42,8 +42,8 @@
 // both, used by the short-K 256-wide layers), double-buffered when two tiles fit in the 512 columns.
 // Variants selected by the host per layer (conv_host.cuh): 1-SM MMA with multicast weights vs cta_group::2, a K-split over filter
 // taps (tap0 / ntaps), and RING > 0: a ring of residual tiles prefetched by TMA for the short-K residual layers.
-// DT_CONV_EPI_SLOTS (2 staging slots per epilogue group) and DT_CONV_WARPS_NARROW (8 converter warps) are measured-and-rejected
-// experiment switches kept for the next round's tuning.
+// SLOTS: staging slots per epilogue group (1 or 2, picked per layer by the host).  DT_CONV_WARPS_NARROW (8 converter warps) is a
+// measured-and-rejected experiment switch.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -53,15 +53,10 @@ namespace dt {
 
 enum ConvResidualMode { RES_NONE = 0, RES_TILE = 1, RES_UPSAMPLE2X = 2 };
 enum ConvKind { KIND_TF32X3 = 0, KIND_F16X3 = 1 };
-#ifndef DT_CONV_EPI_SLOTS
-#define DT_CONV_EPI_SLOTS 1
-#endif
 #ifndef DT_CONV_WARPS_NARROW
 #define DT_CONV_WARPS_NARROW 4
 #endif
-#ifndef DT_CONV_RING_SLOTS
-#define DT_CONV_RING_SLOTS 1       // epilogue staging slots per group in the residual-ring variant
-#endif
+
 
 struct ConvParams {
     CUtensorMap tm_a;      // 4D {C, W, H, N} over the NHWC input (elementStrides carry the conv stride)
@@ -96,7 +91,7 @@ struct ConvParams {
     int pdl;               // launched with programmatic stream serialization: release the next launch early, wait for the previous one
 };
 
-template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND, int RING = 0>
+template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND, int RING = 0, int SLOTS = 1>
 struct ConvCfg {
     static constexpr int BLOCK_M = 128;
     static constexpr int BLOCK_K = 32;
@@ -107,10 +102,13 @@ struct ConvCfg {
     static constexpr int B_BYTES = (kTwoSM ? BLOCK_N / 2 : BLOCK_N) * B_ROW_BYTES;
     // tf32: A, A_lo, B_hi, B_lo.   f16: A (fp32 staging), A_h + A_l (8 KB each, in the second 16 KB), B_h, B_l
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    // epilogue staging: each of the two epilogue groups owns EPI_SLOTS 16 KB slots (128 rows x 32 channels).  Two slots per group let
-    // the residual tile of the next chunk (RES_TILE) arrive, and the previous chunk's store drain, while the current chunk is computed;
-    // they are taken whenever at least 3 pipeline stages still fit beside them.
-    static constexpr int EPI_SLOTS = RING > 0 ? DT_CONV_RING_SLOTS : (((196608 - 2 * A_BYTES) / STAGE_BYTES >= 3) ? DT_CONV_EPI_SLOTS : 1);
+    // epilogue staging: each of the two epilogue groups owns EPI_SLOTS 16 KB slots (128 rows x 32 channels).  With ONE slot the group's
+    // per-chunk chain is  TMEM load -> scale/shift/residual -> staging -> TMA store -> wait until the store has READ the slot -> next chunk;
+    // with TWO slots the store of chunk i drains while chunk i+1 is computed.  Measured per layer (profiles/r02_ab_epilogue_slots.md):
+    // two slots cut the epilogue-bound launches by 10-16 % (K <= 256 at 256 channels: downsample 1x1, deconv GEMMs, the conv3 + residual
+    // layers; every <= 128-wide layer, where the extra 32 KB do not cost a pipeline stage), but cost the long-K 256-wide layers their
+    // fourth pipeline stage (+6-15 %): the host picks SLOTS per layer (conv_host.cuh).
+    static constexpr int EPI_SLOTS = SLOTS;
     // RING > 0 (short-K residual layers, where the epilogue IS the kernel): a ring of RING residual tiles per epilogue group is
     // prefetched by TMA RING chunks ahead, so the HBM latency of the residual never sits in the per-chunk chain; the mainloop
     // (<= 16 k-blocks per tile) makes do with two pipeline stages.
@@ -136,9 +134,9 @@ struct ConvCfg {
     static_assert(8 * (NUM_BARS + 1) <= 256, "barrier area");
 };
 
-template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND, int RING = 0>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NMAIN, kTwoSM, KIND, RING>::THREADS), 1) conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
-    using Cfg = ConvCfg<BLOCK_N, NMAIN, kTwoSM, KIND, RING>;
+template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND, int RING = 0, int SLOTS = 1>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NMAIN, kTwoSM, KIND, RING, SLOTS>::THREADS), 1) conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
+    using Cfg = ConvCfg<BLOCK_N, NMAIN, kTwoSM, KIND, RING, SLOTS>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int NBUF = Cfg::NBUF;
     extern __shared__ uint8_t smem_raw[];

@@ -210,7 +210,186 @@ struct RpnParams {
     int* out_counts;         // [B, L]
     // optional teacher-forcing taps (may be null)
     int* dbg_order;          // [B, L, pre_nms] flat anchor index of the sorted top-k
+    // multi-CTA selection (rpn_select_*_kernel): per (image, level) two 2048-bin digit histograms, per-chunk selected counts, (b1, b2, total)
+    uint32_t* sel_hist;      // [B, L, 2, 2048], zeroed before every run
+    int* sel_chunk_counts;   // [B, L, kRpnMaxChunks]
+    int* sel_info;           // [B, L, 4]: b1, b2, total (-1: not narrowed -> full sort), unused
+    int split;               // 1: selection done by the multi-CTA kernels, rpn_proposals_kernel only finishes
 };
+static constexpr int kRpnChunk = 4096;        // anchors per CTA of the selection kernels (1024 threads x 4)
+static constexpr int kRpnMaxChunks = 64;      // >= ceil(largest level / kRpnChunk): 182 400 / 4096 = 45 at 800x1216; levels above this use the one-CTA path
+
+__host__ __device__ __forceinline__ bool rpn_level_selects(int n, int K) { return n > 4 * K && n > 8192; }
+
+// first bin with c0 + prefix >= K among 2048 bins (warp-collective, all 32 lanes of ONE warp must call); h may be global or shared
+__device__ __forceinline__ void rpn_find_bin(const uint32_t* h, uint32_t c0, uint32_t K, uint32_t* out_bin, uint32_t* out_c) {
+    const int lane = threadIdx.x & 31;
+    uint32_t sum = 0;
+    for (int t = 0; t < 64; ++t) sum += h[lane * 64 + t];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    const uint32_t excl = c0 + incl - sum;
+    const bool hit = excl + sum >= K;
+    const unsigned hits = __ballot_sync(0xffffffffu, hit);
+    const uint32_t all = __shfl_sync(0xffffffffu, incl, 31);
+    if (hits == 0) { if (lane == 0) { *out_bin = 2048; *out_c = c0 + all; } }
+    else if (lane == __ffs(hits) - 1) {
+        uint32_t c = excl, bb = (uint32_t)lane * 64;
+        for (; bb < (uint32_t)lane * 64 + 64; ++bb) { if (c + h[bb] >= K) break; c += h[bb]; }
+        *out_bin = bb; *out_c = c;
+    }
+}
+
+// ---- selection pass 1: keys in (H,W,A) order + first-level digit histogram.  grid (chunks, L, B), 1024 threads.
+static __global__ void __launch_bounds__(1024) rpn_select_keys_kernel(const __grid_constant__ RpnParams P) {
+    __shared__ uint32_t hist[2048];
+    const int l = blockIdx.y, b = blockIdx.z;
+    const RpnLevel& lv = P.lv[l];
+    const int n = lv.n, i0 = blockIdx.x * kRpnChunk;
+    if (i0 >= n) return;
+    const int K = (P.pre_nms <= 0 || P.pre_nms >= n) ? n : P.pre_nms;
+    const bool select = rpn_level_selects(n, K);
+    uint32_t* k0 = P.k0 + (size_t)b * P.ws_per_image + lv.ws_off;
+    int* v0 = P.v0 + (size_t)b * P.ws_per_image + lv.ws_off;
+    const float* base = lv.rpn_out + (size_t)b * lv.H * lv.W * lv.ch_stride;
+    if (select) { for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0; __syncthreads(); }
+    uint32_t k[4];
+    bool valid[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * 1024 + threadIdx.x;
+        valid[j] = i < n;
+        k[j] = 0u;
+        if (valid[j]) { const int a = i % lv.A, cell = i / lv.A; k[j] = float_desc_key(base[(size_t)cell * lv.ch_stride + a]); }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * 1024 + threadIdx.x;
+        if (valid[j]) { k0[i] = k[j]; v0[i] = i; }
+        if (select) {
+            const unsigned act = __ballot_sync(0xffffffffu, valid[j]);
+            if (valid[j]) {
+                const uint32_t d = k[j] >> 21;
+                const unsigned m = __match_any_sync(act, d);
+                if ((m & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&hist[d], (uint32_t)__popc(m));
+            }
+        }
+    }
+    if (!select) return;
+    __syncthreads();
+    uint32_t* g = P.sel_hist + ((size_t)b * P.num_levels + l) * 4096;
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) if (hist[i]) atomicAdd(&g[i], hist[i]);      // integer counts: order-independent
+}
+
+// ---- selection pass 2: second-level digit histogram inside the boundary bin b1
+static __global__ void __launch_bounds__(1024) rpn_select_hist2_kernel(const __grid_constant__ RpnParams P) {
+    __shared__ uint32_t hist[2048];
+    __shared__ uint32_t sel[2];
+    const int l = blockIdx.y, b = blockIdx.z;
+    const RpnLevel& lv = P.lv[l];
+    const int n = lv.n, i0 = blockIdx.x * kRpnChunk;
+    if (i0 >= n) return;
+    const int K = (P.pre_nms <= 0 || P.pre_nms >= n) ? n : P.pre_nms;
+    if (!rpn_level_selects(n, K)) return;
+    uint32_t* g = P.sel_hist + ((size_t)b * P.num_levels + l) * 4096;
+    if (threadIdx.x < 32) rpn_find_bin(g, 0u, (uint32_t)K, &sel[0], &sel[1]);
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const uint32_t b1 = sel[0];
+    const uint32_t* k0 = P.k0 + (size_t)b * P.ws_per_image + lv.ws_off;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * 1024 + threadIdx.x;
+        const uint32_t key = i < n ? k0[i] : 0xffffffffu;
+        const bool valid = (i < n) && ((key >> 21) == b1);
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const uint32_t d = (key >> 10) & 2047u;
+            const unsigned m = __match_any_sync(act, d);
+            if ((m & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&hist[d], (uint32_t)__popc(m));
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) if (hist[i]) atomicAdd(&g[2048 + i], hist[i]);
+}
+
+// ---- selection pass 3: per-chunk count of the selected keys; chunk 0 publishes (b1, b2, total)
+static __global__ void __launch_bounds__(1024) rpn_select_count_kernel(const __grid_constant__ RpnParams P) {
+    __shared__ uint32_t sel[4];
+    __shared__ int scratch[33];
+    const int l = blockIdx.y, b = blockIdx.z;
+    const RpnLevel& lv = P.lv[l];
+    const int n = lv.n, i0 = blockIdx.x * kRpnChunk;
+    if (i0 >= n) return;
+    const int K = (P.pre_nms <= 0 || P.pre_nms >= n) ? n : P.pre_nms;
+    if (!rpn_level_selects(n, K)) return;
+    const uint32_t* g = P.sel_hist + ((size_t)b * P.num_levels + l) * 4096;
+    if (threadIdx.x < 32) {
+        rpn_find_bin(g, 0u, (uint32_t)K, &sel[0], &sel[1]);
+        __syncwarp();
+        rpn_find_bin(g + 2048, sel[1], (uint32_t)K, &sel[2], &sel[3]);
+        __syncwarp();
+        if (threadIdx.x == 0 && sel[2] < 2048u) sel[3] += g[2048 + sel[2]];
+    }
+    __syncthreads();
+    const uint32_t b1 = sel[0], b2 = sel[2], total = sel[3];
+    int* info = P.sel_info + ((size_t)b * P.num_levels + l) * 4;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { info[0] = (int)b1; info[1] = (int)b2; info[2] = total <= 8192u ? (int)total : -1; }
+    if (total > 8192u) return;
+    const uint32_t* k0 = P.k0 + (size_t)b * P.ws_per_image + lv.ws_off;
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = i0 + 4 * threadIdx.x + j;
+        if (i < n) { const uint32_t key = k0[i], d1 = key >> 21; cnt += ((d1 < b1) || (d1 == b1 && ((key >> 10) & 2047u) <= b2)) ? 1 : 0; }
+    }
+    int tot;
+    block_rank_count(cnt, scratch, &tot);
+    if (threadIdx.x == 0) P.sel_chunk_counts[((size_t)b * P.num_levels + l) * kRpnMaxChunks + blockIdx.x] = tot;
+}
+
+// ---- selection pass 4: ordered compaction (ascending anchor index, like the one-CTA path) into (k1, v1)
+static __global__ void __launch_bounds__(1024) rpn_select_scatter_kernel(const __grid_constant__ RpnParams P) {
+    __shared__ int scratch[33];
+    __shared__ int offset;
+    const int l = blockIdx.y, b = blockIdx.z;
+    const RpnLevel& lv = P.lv[l];
+    const int n = lv.n, i0 = blockIdx.x * kRpnChunk;
+    if (i0 >= n) return;
+    const int K = (P.pre_nms <= 0 || P.pre_nms >= n) ? n : P.pre_nms;
+    if (!rpn_level_selects(n, K)) return;
+    const int* info = P.sel_info + ((size_t)b * P.num_levels + l) * 4;
+    if (info[2] < 0) return;
+    const uint32_t b1 = (uint32_t)info[0], b2 = (uint32_t)info[1];
+    if (threadIdx.x == 0) {
+        const int* cc = P.sel_chunk_counts + ((size_t)b * P.num_levels + l) * kRpnMaxChunks;
+        int o = 0;
+        for (int c = 0; c < (int)blockIdx.x; ++c) o += cc[c];
+        offset = o;
+    }
+    __syncthreads();
+    const uint32_t* k0 = P.k0 + (size_t)b * P.ws_per_image + lv.ws_off;
+    uint32_t* k1 = P.k1 + (size_t)b * P.ws_per_image + lv.ws_off;
+    int* v1 = P.v1 + (size_t)b * P.ws_per_image + lv.ws_off;
+    uint32_t k[4];
+    bool f[4];
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = i0 + 4 * threadIdx.x + j;
+        k[j] = i < n ? k0[i] : 0xffffffffu;
+        const uint32_t d1 = k[j] >> 21;
+        f[j] = (i < n) && ((d1 < b1) || (d1 == b1 && ((k[j] >> 10) & 2047u) <= b2));
+        cnt += f[j] ? 1 : 0;
+    }
+    int tot;
+    int r = offset + block_rank_count(cnt, scratch, &tot);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (f[j]) { k1[r] = k[j]; v1[r] = i0 + 4 * threadIdx.x + j; ++r; }
+}
+
 
 // grid (L, B), 1024 threads
 static __global__ void __launch_bounds__(1024) rpn_proposals_kernel(const __grid_constant__ RpnParams P) {
@@ -234,122 +413,136 @@ static __global__ void __launch_bounds__(1024) rpn_proposals_kernel(const __grid
     const int K = (P.pre_nms <= 0 || P.pre_nms >= n) ? n : P.pre_nms;
     const int* vs = v0;                 // sorted anchor indices end up here
     bool narrowed = false;
-    const bool select = n > 4 * K && n > 8192;
-    uint32_t* h1 = hist;                // 2048 bins
-    uint32_t* h2 = hist + 2048;         // 2048 bins
-    __shared__ uint32_t sel[4];         // b1, c1, b2, count
-    if (select) {
-        for (int i = threadIdx.x; i < 4096; i += blockDim.x) hist[i] = 0;
-        __syncthreads();
-    }
-    for (int base_i = 0; base_i < n; base_i += 4 * blockDim.x) {
-        uint32_t k[4];
-        bool valid[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int i = base_i + j * blockDim.x + threadIdx.x;
-            valid[j] = i < n;
-            k[j] = 0u;
-            if (valid[j]) {
-                const int a = i % lv.A, cell = i / lv.A;
-                k[j] = float_desc_key(base[(size_t)cell * lv.ch_stride + a]);
+    // P.split: the keys, the two-level radix select and the ordered compaction were done at full-GPU width by rpn_select_*_kernel
+    // (one CTA per 4096 anchors instead of one CTA per level: the 182 400-anchor P2 level was the long pole of this kernel); (k1, v1)
+    // hold the `total` selected (key, index) pairs in ascending index order, (k0, v0) all keys.  What remains is per (level, image).
+    if (P.split && n <= kRpnChunk * kRpnMaxChunks) {
+        if (rpn_level_selects(n, K)) {
+            const int total = P.sel_info[((size_t)b * P.num_levels + l) * 4 + 2];
+            if (total >= 0) {
+                block_radix_sort_asc_u32(k1, v1, k0, v0, total, hist);
+                vs = v1;
+                narrowed = true;
             }
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int i = base_i + j * blockDim.x + threadIdx.x;
-            if (valid[j]) { k0[i] = k[j]; v0[i] = i; }
-            if (select) {
-                // objectness scores cluster in a few exponent bins: aggregate equal digits inside the warp before touching shared memory
-                const unsigned act = __ballot_sync(0xffffffffu, valid[j]);
-                if (valid[j]) {
-                    const uint32_t d = k[j] >> 21;
-                    const unsigned m = __match_any_sync(act, d);
-                    if ((m & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&h1[d], (uint32_t)__popc(m));
-                }
-            }
+    } else {
+        const bool select = n > 4 * K && n > 8192;
+        uint32_t* h1 = hist;                // 2048 bins
+        uint32_t* h2 = hist + 2048;         // 2048 bins
+        __shared__ uint32_t sel[4];         // b1, c1, b2, count
+        if (select) {
+            for (int i = threadIdx.x; i < 4096; i += blockDim.x) hist[i] = 0;
+            __syncthreads();
         }
-    }
-    __syncthreads();
-    // first bin b with c + h[b] >= K (c = keys in the bins before it), by warp 0: 64 bins per lane, warp prefix, serial scan of one lane's bins
-    auto find_bin = [&](const uint32_t* h, uint32_t c0, uint32_t* out_bin, uint32_t* out_c) {
-        if (threadIdx.x < 32) {
-            const int lane = threadIdx.x;
-            uint32_t sum = 0;
-            for (int t = 0; t < 64; ++t) sum += h[lane * 64 + t];
-            uint32_t incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            const uint32_t excl = c0 + incl - sum;
-            const bool hit = excl + sum >= (uint32_t)K;            // the crossing lies in or before this lane's bins
-            const unsigned hits = __ballot_sync(0xffffffffu, hit);
-            if (hits == 0) { if (lane == 0) { *out_bin = 2048; *out_c = c0 + __shfl_sync(0xffffffffu, incl, 31); } }
-            else if (lane == __ffs(hits) - 1) {
-                uint32_t c = excl, bb = (uint32_t)lane * 64;
-                for (; bb < (uint32_t)lane * 64 + 64; ++bb) { if (c + h[bb] >= (uint32_t)K) break; c += h[bb]; }
-                *out_bin = bb; *out_c = c;
-            }
-        }
-    };
-    if (select) {
-        find_bin(h1, 0u, &sel[0], &sel[1]);
-        __syncthreads();
-        const uint32_t b1 = sel[0], c1 = sel[1];
         for (int base_i = 0; base_i < n; base_i += 4 * blockDim.x) {
             uint32_t k[4];
-#pragma unroll
+            bool valid[4];
+    #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int i = base_i + j * blockDim.x + threadIdx.x;
-                k[j] = i < n ? k0[i] : 0xffffffffu;
+                valid[j] = i < n;
+                k[j] = 0u;
+                if (valid[j]) {
+                    const int a = i % lv.A, cell = i / lv.A;
+                    k[j] = float_desc_key(base[(size_t)cell * lv.ch_stride + a]);
+                }
             }
-#pragma unroll
+    #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int i = base_i + j * blockDim.x + threadIdx.x;
-                const bool valid = (i < n) && ((k[j] >> 21) == b1);
-                const unsigned act = __ballot_sync(0xffffffffu, valid);
-                if (valid) {
-                    const uint32_t d = (k[j] >> 10) & 2047u;
-                    const unsigned m = __match_any_sync(act, d);
-                    if ((m & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&h2[d], (uint32_t)__popc(m));
+                if (valid[j]) { k0[i] = k[j]; v0[i] = i; }
+                if (select) {
+                    // objectness scores cluster in a few exponent bins: aggregate equal digits inside the warp before touching shared memory
+                    const unsigned act = __ballot_sync(0xffffffffu, valid[j]);
+                    if (valid[j]) {
+                        const uint32_t d = k[j] >> 21;
+                        const unsigned m = __match_any_sync(act, d);
+                        if ((m & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&h1[d], (uint32_t)__popc(m));
+                    }
                 }
             }
         }
         __syncthreads();
-        find_bin(h2, c1, &sel[2], &sel[3]);
-        __syncthreads();
-        if (threadIdx.x == 0 && sel[2] < 2048u) sel[3] += h2[sel[2]];
-        __syncthreads();
-        const uint32_t b2 = sel[2], total = sel[3];
-        if (total <= 8192u) {
-            // ordered compaction: a thread owns 4 consecutive indices, one block scan per 4096 keys
-            int m = 0;
+        // first bin b with c + h[b] >= K (c = keys in the bins before it), by warp 0: 64 bins per lane, warp prefix, serial scan of one lane's bins
+        auto find_bin = [&](const uint32_t* h, uint32_t c0, uint32_t* out_bin, uint32_t* out_c) {
+            if (threadIdx.x < 32) {
+                const int lane = threadIdx.x;
+                uint32_t sum = 0;
+                for (int t = 0; t < 64; ++t) sum += h[lane * 64 + t];
+                uint32_t incl = sum;
+    #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                const uint32_t excl = c0 + incl - sum;
+                const bool hit = excl + sum >= (uint32_t)K;            // the crossing lies in or before this lane's bins
+                const unsigned hits = __ballot_sync(0xffffffffu, hit);
+                if (hits == 0) { if (lane == 0) { *out_bin = 2048; *out_c = c0 + __shfl_sync(0xffffffffu, incl, 31); } }
+                else if (lane == __ffs(hits) - 1) {
+                    uint32_t c = excl, bb = (uint32_t)lane * 64;
+                    for (; bb < (uint32_t)lane * 64 + 64; ++bb) { if (c + h[bb] >= (uint32_t)K) break; c += h[bb]; }
+                    *out_bin = bb; *out_c = c;
+                }
+            }
+        };
+        if (select) {
+            find_bin(h1, 0u, &sel[0], &sel[1]);
+            __syncthreads();
+            const uint32_t b1 = sel[0], c1 = sel[1];
             for (int base_i = 0; base_i < n; base_i += 4 * blockDim.x) {
-                const int i0 = base_i + 4 * threadIdx.x;
                 uint32_t k[4];
-                bool f[4];
-                int cnt = 0;
-#pragma unroll
+    #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int i = i0 + j;
+                    const int i = base_i + j * blockDim.x + threadIdx.x;
                     k[j] = i < n ? k0[i] : 0xffffffffu;
                 }
-#pragma unroll
+    #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const uint32_t d1 = k[j] >> 21;
-                    f[j] = (i0 + j < n) && ((d1 < b1) || (d1 == b1 && ((k[j] >> 10) & 2047u) <= b2));
-                    cnt += f[j] ? 1 : 0;
+                    const int i = base_i + j * blockDim.x + threadIdx.x;
+                    const bool valid = (i < n) && ((k[j] >> 21) == b1);
+                    const unsigned act = __ballot_sync(0xffffffffu, valid);
+                    if (valid) {
+                        const uint32_t d = (k[j] >> 10) & 2047u;
+                        const unsigned m = __match_any_sync(act, d);
+                        if ((m & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&h2[d], (uint32_t)__popc(m));
+                    }
                 }
-                int tot;
-                int r = m + block_rank_count(cnt, scratch, &tot);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (f[j]) { k1[r] = k[j]; v1[r] = i0 + j; ++r; }
-                m += tot;
             }
             __syncthreads();
-            block_radix_sort_asc_u32(k1, v1, k0, v0, m, hist);
-            vs = v1;
-            narrowed = true;
+            find_bin(h2, c1, &sel[2], &sel[3]);
+            __syncthreads();
+            if (threadIdx.x == 0 && sel[2] < 2048u) sel[3] += h2[sel[2]];
+            __syncthreads();
+            const uint32_t b2 = sel[2], total = sel[3];
+            if (total <= 8192u) {
+                // ordered compaction: a thread owns 4 consecutive indices, one block scan per 4096 keys
+                int m = 0;
+                for (int base_i = 0; base_i < n; base_i += 4 * blockDim.x) {
+                    const int i0 = base_i + 4 * threadIdx.x;
+                    uint32_t k[4];
+                    bool f[4];
+                    int cnt = 0;
+    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = i0 + j;
+                        k[j] = i < n ? k0[i] : 0xffffffffu;
+                    }
+    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t d1 = k[j] >> 21;
+                        f[j] = (i0 + j < n) && ((d1 < b1) || (d1 == b1 && ((k[j] >> 10) & 2047u) <= b2));
+                        cnt += f[j] ? 1 : 0;
+                    }
+                    int tot;
+                    int r = m + block_rank_count(cnt, scratch, &tot);
+    #pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (f[j]) { k1[r] = k[j]; v1[r] = i0 + j; ++r; }
+                    m += tot;
+                }
+                __syncthreads();
+                block_radix_sort_asc_u32(k1, v1, k0, v0, m, hist);
+                vs = v1;
+                narrowed = true;
+            }
         }
     }
     if (!narrowed) block_radix_sort_asc_u32(k0, v0, k1, v1, n, hist);
