@@ -284,16 +284,17 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
         L->ring = (use_ring && L->nmain == 0 && L->two_sm && L->kind == KIND_F16X3 && s.res_mode == RES_TILE && p.ntaps * p.cin_blocks <= 8) ? 1 : 0;
     }
     {
-        // Two staging slots per epilogue group wherever they do not cost a pipeline stage that the layer needs: every tile up to 128 wide
-        // (their stages are 40 KB: four still fit), and the 256-wide layers with at most 8 k-blocks per tile (K <= 256), whose time is the
-        // epilogue.  Long-K 256-wide layers keep one slot and four stages.  The residual-ring variant then runs ring 2 + slots 2 instead
-        // of ring 3 + slot 1 (-10 % on the conv3 + residual layers).  DT_CONV_SLOTS=1|2 forces one setting (A/B, tests).
+        // Two staging slots per epilogue group (the TMA store of a chunk drains while the next chunk is computed: -10..16 % on the
+        // epilogue-bound layers) wherever the epilogue is exposed: every tile up to 128 wide, the 256-wide layers with at most 16 k-blocks
+        // per tile (K <= 512), and the 256-wide layers that cannot double-buffer their accumulators (NMAIN = 1: the mask-head K-split
+        // halves, whose epilogue is never overlapped by the next tile's MMAs).  Long-K merged-accumulator layers hide their epilogue behind
+        // the next tile and keep one slot = one more pipeline stage.  With the in-place fp16 split a stage is 32 KB, so even two slots
+        // leave five stages.  DT_CONV_SLOTS=1|2 forces one setting (A/B, tests).
         static int force = -1;
         if (force < 0) { const char* e = getenv("DT_CONV_SLOTS"); force = e ? atoi(e) : 0; }
         const int kb = p.ntaps * p.cin_blocks;
-        L->slots = (bn <= 128 || (bn == 256 && L->nmain == 0 && kb <= 8)) ? 2 : 1;
-        if (force == 1) L->slots = 1;
-        if (force == 2 && !(bn == 256 && L->nmain != 0)) L->slots = 2;
+        L->slots = (bn <= 128 || (bn == 256 && (L->nmain != 0 || kb <= 16))) ? 2 : 1;
+        if (force == 1 || force == 2) L->slots = force;
     }
     return true;
 }
@@ -371,12 +372,16 @@ inline cudaError_t conv_launch_cfg(const ConvLayer& L, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-// residual prefetch ring depth of the short-K residual layers: 3 tiles with one staging slot per group, 2 tiles with two slots
-constexpr int kConvResRing1 = 3, kConvResRing2 = 2;
+// residual prefetch ring of the short-K residual layers (conv3 of the bottlenecks): tiles in flight per epilogue group (DT_CONV_RING=2|3)
+inline int conv_ring_depth() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DT_CONV_RING"); v = (e && e[0] == '2') ? 2 : 3; }
+    return v;
+}
 
 template <bool TWO, int KIND>
 inline cudaError_t conv_launch_sm(const ConvLayer& L, cudaStream_t stream) {
-    // two staging slots only in the kind::f16 kernels (the engine default): the tf32 kind's stages are twice as large
+    // two staging slots only in the kind::f16 kernels (the engine default): the tf32 kind's stages are 64-96 KB
     constexpr bool kCan2 = KIND == KIND_F16X3;
     const bool s2 = kCan2 && L.slots == 2;
     constexpr int S2 = kCan2 ? 2 : 1;
@@ -388,11 +393,15 @@ inline cudaError_t conv_launch_sm(const ConvLayer& L, cudaStream_t stream) {
         case 256:
             if (L.nmain == 0) {
                 if constexpr (TWO && KIND == KIND_F16X3) {
-                    if (L.ring) return s2 ? conv_launch_cfg<256, 0, TWO, KIND, kConvResRing2, 2>(L, stream) : conv_launch_cfg<256, 0, TWO, KIND, kConvResRing1, 1>(L, stream);
+                    if (L.ring) {
+                        if (!s2) return conv_launch_cfg<256, 0, TWO, KIND, 3, 1>(L, stream);
+                        return conv_ring_depth() == 2 ? conv_launch_cfg<256, 0, TWO, KIND, 2, 2>(L, stream) : conv_launch_cfg<256, 0, TWO, KIND, 3, 2>(L, stream);
+                    }
+                    if (s2) return conv_launch_cfg<256, 0, TWO, KIND, 0, 2>(L, stream);
                 }
-                if constexpr (TWO && KIND == KIND_F16X3) { if (s2) return conv_launch_cfg<256, 0, TWO, KIND, 0, 2>(L, stream); }
                 return conv_launch_cfg<256, 0, TWO, KIND, 0, 1>(L, stream);
             }
+            if constexpr (TWO && KIND == KIND_F16X3) { if (s2) return conv_launch_cfg<256, 1, TWO, KIND, 0, 2>(L, stream); }
             return conv_launch_cfg<256, 1, TWO, KIND>(L, stream);
         default: return cudaErrorInvalidValue;
     }

@@ -100,8 +100,13 @@ struct ConvCfg {
     // 2-SM MMA (cta_group::2): every CTA holds only ITS half -> smaller stages, deeper pipeline, half the operand ingest per SM.
     static constexpr int B_ROW_BYTES = KIND == KIND_F16X3 ? 64 : 128; // 32 k-elements per row
     static constexpr int B_BYTES = (kTwoSM ? BLOCK_N / 2 : BLOCK_N) * B_ROW_BYTES;
-    // tf32: A, A_lo, B_hi, B_lo.   f16: A (fp32 staging), A_h + A_l (8 KB each, in the second 16 KB), B_h, B_l
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    // tf32: A, A_lo (16 KB each), B_hi, B_lo.
+    // f16 : ONE 16 KB A area.  TMA delivers the fp32 tile into it; the converter warps read their rows into registers, meet at a named
+    //       barrier and write A_h | A_l (8 KB each) IN PLACE over the fp32 data (the two fp16 tiles are exactly as large as the fp32 tile);
+    //       with a_planes TMA delivers A_h | A_l there directly.  A stage is 32 KB instead of 48 KB: 5-6 pipeline stages instead of 3-4,
+    //       i.e. more bytes in flight for the layers that are bound by HBM latency x bandwidth, and room for two epilogue slots everywhere.
+    static constexpr int A_STAGE_BYTES = KIND == KIND_F16X3 ? A_BYTES : 2 * A_BYTES;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + 2 * B_BYTES;
     // epilogue staging: each of the two epilogue groups owns EPI_SLOTS 16 KB slots (128 rows x 32 channels).  With ONE slot the group's
     // per-chunk chain is  TMEM load -> scale/shift/residual -> staging -> TMA store -> wait until the store has READ the slot -> next chunk;
     // with TWO slots the store of chunk i drains while chunk i+1 is computed.  Measured per layer (profiles/r02_ab_epilogue_slots.md):
@@ -115,7 +120,7 @@ struct ConvCfg {
     static constexpr int RING_BYTES = 2 * RING * A_BYTES;
     static constexpr int EPI_BYTES = 2 * EPI_SLOTS * A_BYTES;
     static constexpr int STAGES_FIT = (196608 + 2 * A_BYTES - EPI_BYTES - RING_BYTES) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_FIT > 4 ? 4 : STAGES_FIT;
+    static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
     static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
     static_assert(STAGES >= 2, "pipeline too shallow");
     static constexpr int TILE_COLS = (NMAIN + 1) * BLOCK_N;          // TMEM columns of one tile's accumulators
@@ -234,8 +239,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                     mbar_arrive_expect_tx(bar_full(s), tx_bytes);
                     if (KIND == KIND_F16X3 && p.a_planes) {
                         // fp16 planes: the two operand tiles land where the converters would have written them
-                        tma_load_4d(st + Cfg::A_BYTES, &p.tm_a, bar_full(s), cb * 32, w0 * p.stride_w + fx - p.pad_w, h0 * p.stride_h + fy - p.pad_h, n0img);
-                        tma_load_4d(st + Cfg::A_BYTES + Cfg::A_BYTES / 2, &p.tm_a2, bar_full(s), cb * 32, w0 * p.stride_w + fx - p.pad_w,
+                        tma_load_4d(st, &p.tm_a, bar_full(s), cb * 32, w0 * p.stride_w + fx - p.pad_w, h0 * p.stride_h + fy - p.pad_h, n0img);
+                        tma_load_4d(st + Cfg::A_BYTES / 2, &p.tm_a2, bar_full(s), cb * 32, w0 * p.stride_w + fx - p.pad_w,
                                     h0 * p.stride_h + fy - p.pad_h, n0img);
                     } else {
                         tma_load_4d(st, &p.tm_a, bar_full(s), cb * 32, w0 * p.stride_w + fx - p.pad_w, h0 * p.stride_h + fy - p.pad_h, n0img);
@@ -244,14 +249,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                     const int nrow = n0 + (int)cta_rank * (BLOCK_N / 2);
                     if constexpr (kTwoSM) {
                         // 2-SM MMA: the half stays local (the pair's tensor cores read both halves in place)
-                        tma_load_2d(st + 2 * Cfg::A_BYTES, &p.tm_bhi, bar_full(s), kbg * 32, nrow);
-                        if (p.passes == 3) tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &p.tm_blo, bar_full(s), kbg * 32, nrow);
+                        tma_load_2d(st + Cfg::A_STAGE_BYTES, &p.tm_bhi, bar_full(s), kbg * 32, nrow);
+                        if (p.passes == 3) tma_load_2d(st + Cfg::A_STAGE_BYTES + Cfg::B_BYTES, &p.tm_blo, bar_full(s), kbg * 32, nrow);
                     } else {
                         // 1-SM MMA: multicast to both CTAs of the pair
                         const uint32_t half = cta_rank * (Cfg::B_BYTES / 2);
-                        tma_load_2d_mcast(st + 2 * Cfg::A_BYTES + half, &p.tm_bhi, bar_full(s), kbg * 32, nrow, (uint16_t)3);
+                        tma_load_2d_mcast(st + Cfg::A_STAGE_BYTES + half, &p.tm_bhi, bar_full(s), kbg * 32, nrow, (uint16_t)3);
                         if (p.passes == 3)
-                            tma_load_2d_mcast(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + half, &p.tm_blo, bar_full(s), kbg * 32, nrow, (uint16_t)3);
+                            tma_load_2d_mcast(st + Cfg::A_STAGE_BYTES + Cfg::B_BYTES + half, &p.tm_blo, bar_full(s), kbg * 32, nrow, (uint16_t)3);
                     }
                 }
             }
@@ -287,10 +292,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                     const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
                     uint64_t da, dal, dbh, dbl;      // "hi" A, "lo" A, "hi" B, "lo" B
                     if constexpr (KIND == KIND_F16X3) {
-                        da = umma_desc_k_sw64(st + Cfg::A_BYTES);
-                        dal = umma_desc_k_sw64(st + Cfg::A_BYTES + Cfg::A_BYTES / 2);
-                        dbh = umma_desc_k_sw64(st + 2 * Cfg::A_BYTES);
-                        dbl = umma_desc_k_sw64(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+                        da = umma_desc_k_sw64(st);
+                        dal = umma_desc_k_sw64(st + Cfg::A_BYTES / 2);
+                        dbh = umma_desc_k_sw64(st + Cfg::A_STAGE_BYTES);
+                        dbl = umma_desc_k_sw64(st + Cfg::A_STAGE_BYTES + Cfg::B_BYTES);
                     } else {
                         da = umma_desc_k_sw128(st);
                         dal = umma_desc_k_sw128(st + Cfg::A_BYTES);
@@ -339,21 +344,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                 if (KIND == KIND_F16X3 && p.a_planes) {
                     // operand tiles were delivered by TMA (async proxy): nothing to convert, just pass the stage on
                 } else if constexpr (KIND == KIND_F16X3) {
-                    // A_h = fp16(A), A_l = fp16(A - A_h): thread -> (row, 8-channel group); two 16-byte pieces of the 128B-swizzled
-                    // fp32 row in, one 16-byte piece of each 64B-swizzled fp16 row out (both access patterns are conflict-free)
-                    const uint8_t* a32 = smem_gen + s * Cfg::STAGE_BYTES;
-                    uint8_t* ah = smem_gen + s * Cfg::STAGE_BYTES + Cfg::A_BYTES;
+                    // A_h = fp16(A), A_l = fp16(A - A_h), IN PLACE: a thread owns one row -- 8 x 16-byte pieces of the 128B-swizzled fp32 row in
+                    // (registers), then, once every converter thread has read its row (named barrier: the fp16 tiles overlay other threads'
+                    // fp32 rows), 4 x 16-byte pieces of each 64B-swizzled fp16 row out (both access patterns are conflict-free)
+                    uint8_t* a32 = smem_gen + s * Cfg::STAGE_BYTES;
+                    uint8_t* ah = a32;
                     uint8_t* al = ah + Cfg::A_BYTES / 2;
                     bool bad = false;
                     // rows past the TMA box (boxes smaller than 128 pixels) are never written: whatever they hold produces accumulator
                     // rows that are never stored, but it must not trip the range flag
                     const bool live_row = (ct & 127) * 128 < p.a_tile_bytes;
-                    constexpr int PIECES = 4 * 128 / Cfg::CONV_THREADS;        // 16-byte fp16 pieces per thread (4 or 2)
+                    static_assert(Cfg::CONV_THREADS == 128, "the in-place split maps one converter thread to one tile row");
+                    const int r = ct;
+                    float4 fin[8];
 #pragma unroll
-                    for (int i = 0; i < PIECES; ++i) {
-                        const int r = ct & 127, c8 = (ct >> 7) * PIECES + i;
-                        const float4 v0 = *reinterpret_cast<const float4*>(a32 + r * 128 + (((2 * c8) ^ (r & 7)) << 4));
-                        const float4 v1 = *reinterpret_cast<const float4*>(a32 + r * 128 + (((2 * c8 + 1) ^ (r & 7)) << 4));
+                    for (int i = 0; i < 8; ++i) fin[i] = *reinterpret_cast<const float4*>(a32 + r * 128 + ((i ^ (r & 7)) << 4));
+                    named_bar_sync(3, Cfg::CONV_THREADS);          // ids 1, 2 belong to the epilogue groups
+#pragma unroll
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        const float4 v0 = fin[2 * c8], v1 = fin[2 * c8 + 1];
                         const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
                         __half2 hh[4], ll[4];
 #pragma unroll
@@ -481,12 +490,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                     for (int j = 0; j < 8; ++j)
                         rr[j] = (rp != nullptr && ch0 + j * 4 < p.cout) ? __ldg(reinterpret_cast<const float4*>(rp) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                // thread 0 of the group has, at the end of the previous chunk, waited until the store that last used this slot finished
-                // reading it and (RES_TILE) started the TMA load of this chunk's residual tile into it
-                named_bar_sync(1 + g, 128);
+                // the accumulator read does not depend on the staging slot: request it BEFORE the group barrier, so that the TMEM latency
+                // overlaps the wait for thread 0 (slot hand-over / residual issue) instead of following it
                 uint32_t v[32];
                 const uint32_t tbase = tbase0 + (uint32_t)(c * 32);
                 tmem_ld_32x32(tbase, v);
+                // thread 0 of the group has, at the end of the previous chunk, waited until the store that last used this slot finished
+                // reading it and (RES_TILE) started the TMA load of this chunk's residual tile into it
+                named_bar_sync(1 + g, 128);
                 tmem_ld_wait();
 #pragma unroll 1
                 for (int a = 1; a <= NMAIN; ++a) {      // remaining main accumulators, then the cross accumulator

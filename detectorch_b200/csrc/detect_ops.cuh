@@ -293,7 +293,11 @@ static __global__ void __launch_bounds__(1024) rpn_select_hist2_kernel(const __g
     const int K = (P.pre_nms <= 0 || P.pre_nms >= n) ? n : P.pre_nms;
     if (!rpn_level_selects(n, K)) return;
     uint32_t* g = P.sel_hist + ((size_t)b * P.num_levels + l) * 4096;
-    if (threadIdx.x < 32) rpn_find_bin(g, 0u, (uint32_t)K, &sel[0], &sel[1]);
+    // the bin search walks the histogram serially: do it on a shared-memory copy (one coalesced load), not on 64 dependent L2 reads
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = g[i];
+    __syncthreads();
+    if (threadIdx.x < 32) rpn_find_bin(hist, 0u, (uint32_t)K, &sel[0], &sel[1]);
+    __syncthreads();
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     const uint32_t b1 = sel[0];
@@ -318,6 +322,7 @@ static __global__ void __launch_bounds__(1024) rpn_select_hist2_kernel(const __g
 static __global__ void __launch_bounds__(1024) rpn_select_count_kernel(const __grid_constant__ RpnParams P) {
     __shared__ uint32_t sel[4];
     __shared__ int scratch[33];
+    __shared__ uint32_t hh[4096];
     const int l = blockIdx.y, b = blockIdx.z;
     const RpnLevel& lv = P.lv[l];
     const int n = lv.n, i0 = blockIdx.x * kRpnChunk;
@@ -325,12 +330,14 @@ static __global__ void __launch_bounds__(1024) rpn_select_count_kernel(const __g
     const int K = (P.pre_nms <= 0 || P.pre_nms >= n) ? n : P.pre_nms;
     if (!rpn_level_selects(n, K)) return;
     const uint32_t* g = P.sel_hist + ((size_t)b * P.num_levels + l) * 4096;
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) hh[i] = g[i];      // both histograms into shared memory (see rpn_select_hist2_kernel)
+    __syncthreads();
     if (threadIdx.x < 32) {
-        rpn_find_bin(g, 0u, (uint32_t)K, &sel[0], &sel[1]);
+        rpn_find_bin(hh, 0u, (uint32_t)K, &sel[0], &sel[1]);
         __syncwarp();
-        rpn_find_bin(g + 2048, sel[1], (uint32_t)K, &sel[2], &sel[3]);
+        rpn_find_bin(hh + 2048, sel[1], (uint32_t)K, &sel[2], &sel[3]);
         __syncwarp();
-        if (threadIdx.x == 0 && sel[2] < 2048u) sel[3] += g[2048 + sel[2]];
+        if (threadIdx.x == 0 && sel[2] < 2048u) sel[3] += hh[2048 + sel[2]];
     }
     __syncthreads();
     const uint32_t b1 = sel[0], b2 = sel[2], total = sel[3];

@@ -254,14 +254,13 @@ __device__ __forceinline__ AxisBin axis_bin2(float start, int p, float bin, int 
 
 static constexpr int kMaxPooled = 16;     // pooled_height / pooled_width supported by the fast path (7 and 14 in practice)
 
-// NHWC features (multi-level), out [R, PH, PW, C]; one CTA per RoI (grid-stride), threads over (bin, 4-channel group).
-// The gathers come from L2 (the maps of a batch do not fit the L1s), so what bounds this kernel is the number of 16-byte loads an SM keeps
-// in flight.  A fully unrolled 4x4 tap block (16 loads in flight, 106 registers) lost more in occupancy than it gained (round 1: 446 ->
-// 606 us); here TWO tap rows x up to 4 tap columns are requested before the first FMA (8 independent loads per thread) under a 64-register
-// budget (4 CTAs per SM): 4x the bytes in flight of the one-load-at-a-time loop.  Summation order per bin is unchanged (row-major over the
-// merged taps), so the results are bit-identical to the previous kernel and to the shared-memory-map variant.
-static __global__ void __launch_bounds__(256, 4) roi_align_fast_nhwc_kernel(RoiLevels lv, const float* __restrict__ rois, const int* __restrict__ level,
-                                                                            int max_rois, int C, int PH, int PW, float* __restrict__ out) {
+// Measured and rejected (round 2, profiles/r02_summary.md): requesting 2 tap rows x 4 tap columns before the first FMA (8 loads in flight, 61
+// registers, 4 CTAs/SM) made the box-head launch 447 -> 510 us and the mask launch 200 -> 237 us, like round 1's fully unrolled 4x4 variant:
+// the kernel is bound by what the L2 delivers to the SMs (ncu: 1.1 GB DRAM read + 0.75 GB written by the two launches, 2.9 TB/s), not by
+// loads in flight per thread; the plain loop with 8 resident CTAs per SM stays.
+// NHWC features (multi-level), out [R, PH, PW, C]; one CTA per RoI (grid-stride), threads over (bin, 4-channel group)
+static __global__ void __launch_bounds__(256) roi_align_fast_nhwc_kernel(RoiLevels lv, const float* __restrict__ rois, const int* __restrict__ level,
+                                                                         int max_rois, int C, int PH, int PW, float* __restrict__ out) {
     __shared__ AxisBin ytab[kMaxPooled];
     __shared__ AxisBin xtab[kMaxPooled];
     const int C4 = C >> 2;
@@ -279,32 +278,16 @@ static __global__ void __launch_bounds__(256, 4) roi_align_fast_nhwc_kernel(RoiL
         for (int o = threadIdx.x; o < per_roi; o += blockDim.x) {
             const int c4 = o % C4;
             const int bin = o / C4;
-            const AxisBin& by = ytab[bin / PW];            // shared-memory tables, read with compile-time offsets (no local copies)
+            const AxisBin& by = ytab[bin / PW];
             const AxisBin& bx = xtab[bin % PW];
-            const int ny = by.n, nx = bx.n;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int r0 = 0; r0 < 4; r0 += 2) {
-                if (r0 >= ny) break;
-                float4 v[2][4];
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    const float4* rowp = fb + (size_t)by.idx[r0 + rr] * W * C4 + c4;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        v[rr][c] = (r0 + rr < ny && c < nx) ? __ldg(rowp + (size_t)bx.idx[c] * C4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    const float wy = by.w[r0 + rr];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        if (r0 + rr < ny && c < nx) {
-                            const float w = wy * bx.w[c];
-                            acc.x = fmaf(w, v[rr][c].x, acc.x); acc.y = fmaf(w, v[rr][c].y, acc.y);
-                            acc.z = fmaf(w, v[rr][c].z, acc.z); acc.w = fmaf(w, v[rr][c].w, acc.w);
-                        }
-                    }
+            for (int r = 0; r < by.n; ++r) {
+                const float4* rowp = fb + (size_t)by.idx[r] * W * C4 + c4;
+                const float wy = by.w[r];
+                for (int c = 0; c < bx.n; ++c) {
+                    const float4 v = __ldg(rowp + (size_t)bx.idx[c] * C4);
+                    const float w = wy * bx.w[c];
+                    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
                 }
             }
             ob[o] = acc;
