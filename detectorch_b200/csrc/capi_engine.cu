@@ -842,7 +842,7 @@ dt_engine_t dt_engine_create(const dt_engine_config* cfg) {
         return nullptr;
     }
     if (cfg->pre_nms_top_n < 1 || cfg->pre_nms_top_n > 8192 || cfg->post_nms_top_n < 1 || cfg->post_nms_top_n > 1024 || cfg->det_cap < cfg->max_dets ||
-        cfg->num_classes < 2) {
+        cfg->num_classes < 2 || cfg->num_classes > 128) {
         fprintf(stderr, "[detectorch_b200] engine: unsupported proposal/detection limits\n");
         return nullptr;
     }

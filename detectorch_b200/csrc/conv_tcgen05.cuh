@@ -89,6 +89,7 @@ struct ConvParams {
     int out_planes;        // KIND_F16X3: write the output as a pair of fp16 planes (hi = fp16(y), lo = fp16(y - hi)) instead of fp32
     int* range_flag;       // KIND_F16X3: set to 1 when an activation does not fit fp16 (|x| >= 65504 or NaN); may be null
     int pdl;               // launched with programmatic stream serialization: release the next launch early, wait for the previous one
+    int nstages;           // pipeline stages actually cycled through (<= the stages that fit; 0 = all): short-K layers run best with 2-3
 };
 
 template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND, int RING = 0, int SLOTS = 1>
@@ -167,6 +168,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_kb = p.ntaps * p.cin_blocks;
+    const uint32_t nst = (p.nstages > 0 && p.nstages < STAGES) ? (uint32_t)p.nstages : (uint32_t)STAGES;
     const int num_items = p.m_pairs * p.n_tiles;
     const int pair = blockIdx.x >> 1;
     const int num_pairs = gridDim.x >> 1;
@@ -227,8 +229,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                 int w0, h0, n0img, n0;
                 tile_of(item, w0, h0, n0img, n0);
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1u;
+                    const int s = (int)(it % nst);
+                    const uint32_t ph = (it / nst) & 1u;
                     mbar_wait(bar_empty(s), ph ^ 1u);
                     const int tap_l = kb / p.cin_blocks;
                     const int cb = kb - tap_l * p.cin_blocks;
@@ -283,8 +285,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
             tc_fence_after();
             const uint32_t acc0 = tmem_acc + (uint32_t)(buf * Cfg::TILE_COLS);
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1u;
+                const int s = (int)(it % nst);
+                const uint32_t ph = (it / nst) & 1u;
                 if constexpr (kTwoSM) mbar_wait_cluster(bar_conv(s), ph);   // both CTAs' TMA data landed and both converted A tiles are published
                 else mbar_wait(bar_conv(s), ph);      // converters waited on full[s] and published their tiles
                 tc_fence_after();
@@ -338,8 +340,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
         uint32_t it = 0;
         for (int item = pair; item < num_items; item += num_pairs) {
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1u;
+                const int s = (int)(it % nst);
+                const uint32_t ph = (it / nst) & 1u;
                 mbar_wait(bar_full(s), ph);
                 if (KIND == KIND_F16X3 && p.a_planes) {
                     // operand tiles were delivered by TMA (async proxy): nothing to convert, just pass the stage on

@@ -792,34 +792,62 @@ static __global__ void __launch_bounds__(256) det_class_kernel(const __grid_cons
     if (threadIdx.x == 0) P.cls_counts[b * P.NC + j] = kept;
 }
 
-// grid B, 1024 threads: limit to max_dets over all classes (result_utils.py:152-168) and emit
+// grid B, 1024 threads: limit to max_dets over all classes (result_utils.py:152-168) and emit.
+// The kept flags of a class are swept by ONE WARP (ballot + popc over 32 RoIs at a time, no block barriers): class counts -> exclusive
+// class offsets -> ordered writes.  Two such sweeps (gather keys, emit) replace two block-wide scans of the NC*R flags (79 iterations x 3
+// __syncthreads each in round 1: 148 us at batch 8).  Order and arithmetic are unchanged: class-major, ascending RoI index.
 static __global__ void __launch_bounds__(1024) det_limit_kernel(const __grid_constant__ DetParams P) {
     __shared__ uint32_t hist[32 * 256];
-    __shared__ int scratch[33];
+    __shared__ int cls_cnt[128], cls_off[129];
     __shared__ float s_thresh;
     const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const size_t cap = (size_t)P.NC * P.R;
     uint32_t* k0 = P.k0 + b * cap; uint32_t* k1 = P.k1 + b * cap;
     int* v0 = P.v0 + b * cap; int* v1 = P.v1 + b * cap;
     const unsigned char* flag = P.keep_flag + (size_t)b * P.NC * P.R;
-    // gather kept (class-major, RoI ascending)
-    int n = 0;
-    for (int base = P.R; base < (int)cap; base += blockDim.x) {     // class 0 (background) skipped
-        const int i = base + threadIdx.x;
-        const bool f = (i < (int)cap) && flag[i];
-        int tot;
-        const int r = block_rank(f, scratch, &tot);
-        if (f) {
-            const int j = i / P.R, ri = i - j * P.R;
-            k0[n + r] = float_desc_key(P.cls[((size_t)b * P.R + ri) * P.NC + j]);
-            v0[n + r] = i;
+    const unsigned lt = (1u << lane) - 1u;
+    // exclusive offsets of the classes from per-class counts (class 0 = background: empty); returns the total
+    auto scan_classes = [&]() {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int o = 0;
+            for (int j = 0; j < P.NC; ++j) { cls_off[j] = o; o += cls_cnt[j]; }
+            cls_off[P.NC] = o;
         }
-        n += tot;
-    }
+        __syncthreads();
+        return cls_off[P.NC];
+    };
+    // sweep 1: kept per class
+    if (threadIdx.x < 128) cls_cnt[threadIdx.x] = 0;
     __syncthreads();
+    for (int j = 1 + warp; j < P.NC; j += nwarps) {
+        int c = 0;
+        for (int base = 0; base < P.R; base += 32) {
+            const int ri = base + lane;
+            c += __popc(__ballot_sync(0xffffffffu, ri < P.R && flag[(size_t)j * P.R + ri]));
+        }
+        if (lane == 0) cls_cnt[j] = c;
+    }
+    const int n = scan_classes();
     float thresh = -INFINITY;
     if (P.max_dets > 0 && n > P.max_dets) {
-        // image_thresh = np.sort(image_scores)[-max_dets]  == max_dets-th largest
+        // image_thresh = np.sort(image_scores)[-max_dets]  == max_dets-th largest: gather the kept scores (class-major, RoI ascending), sort
+        for (int j = 1 + warp; j < P.NC; j += nwarps) {
+            int o = cls_off[j];
+            for (int base = 0; base < P.R; base += 32) {
+                const int ri = base + lane;
+                const bool f = ri < P.R && flag[(size_t)j * P.R + ri];
+                const unsigned m = __ballot_sync(0xffffffffu, f);
+                if (f) {
+                    const int pos = o + __popc(m & lt);
+                    k0[pos] = float_desc_key(P.cls[((size_t)b * P.R + ri) * P.NC + j]);
+                    v0[pos] = j * P.R + ri;
+                }
+                o += __popc(m);
+            }
+        }
+        __syncthreads();
         block_radix_sort_asc_u32(k0, v0, k1, v1, n, hist);
         if (threadIdx.x == 0) {
             const int i = v0[P.max_dets - 1];
@@ -828,31 +856,39 @@ static __global__ void __launch_bounds__(1024) det_limit_kernel(const __grid_con
         }
         __syncthreads();
         thresh = s_thresh;
+        // sweep 2: per class, how many of the kept pass score >= thresh (:162)
+        __syncthreads();
+        for (int j = 1 + warp; j < P.NC; j += nwarps) {
+            int c = 0;
+            for (int base = 0; base < P.R; base += 32) {
+                const int ri = base + lane;
+                const bool f = ri < P.R && flag[(size_t)j * P.R + ri] && P.cls[((size_t)b * P.R + ri) * P.NC + j] >= thresh;
+                c += __popc(__ballot_sync(0xffffffffu, f));
+            }
+            if (lane == 0) cls_cnt[j] = c;
+        }
     }
-    // emit in class-major / RoI-ascending order, score >= thresh (:162)
-    int nout = 0;
-    for (int base = P.R; base < (int)cap; base += blockDim.x) {
-        const int i = base + threadIdx.x;
-        bool f = false;
-        float sc = 0.f;
-        int j = 0, ri = 0;
-        if (i < (int)cap && flag[i]) {
-            j = i / P.R; ri = i - j * P.R;
-            sc = P.cls[((size_t)b * P.R + ri) * P.NC + j];
-            f = sc >= thresh;
+    const int nout = scan_classes();
+    // emit in class-major / RoI-ascending order
+    for (int j = 1 + warp; j < P.NC; j += nwarps) {
+        int o = cls_off[j];
+        for (int base = 0; base < P.R; base += 32) {
+            const int ri = base + lane;
+            bool f = ri < P.R && flag[(size_t)j * P.R + ri];
+            float sc = 0.f;
+            if (f) { sc = P.cls[((size_t)b * P.R + ri) * P.NC + j]; f = sc >= thresh; }
+            const unsigned m = __ballot_sync(0xffffffffu, f);
+            const int pos = o + __popc(m & lt);
+            if (f && pos < P.out_cap) {
+                const float4 bx = P.dec_box[((size_t)b * P.NC + j) * P.R + ri];
+                float* ob = P.out_boxes + ((size_t)b * P.out_cap + pos) * 4;
+                ob[0] = bx.x; ob[1] = bx.y; ob[2] = bx.z; ob[3] = bx.w;
+                P.out_scores[(size_t)b * P.out_cap + pos] = sc;
+                P.out_classes[(size_t)b * P.out_cap + pos] = j;
+                P.out_roi_idx[(size_t)b * P.out_cap + pos] = ri;
+            }
+            o += __popc(m);
         }
-        int tot;
-        const int r = block_rank(f, scratch, &tot);
-        const int pos = nout + r;
-        if (f && pos < P.out_cap) {
-            const float4 bx = P.dec_box[((size_t)b * P.NC + j) * P.R + ri];
-            float* ob = P.out_boxes + ((size_t)b * P.out_cap + pos) * 4;
-            ob[0] = bx.x; ob[1] = bx.y; ob[2] = bx.z; ob[3] = bx.w;
-            P.out_scores[(size_t)b * P.out_cap + pos] = sc;
-            P.out_classes[(size_t)b * P.out_cap + pos] = j;
-            P.out_roi_idx[(size_t)b * P.out_cap + pos] = ri;
-        }
-        nout += tot;
     }
     for (int i = min(nout, P.out_cap) + threadIdx.x; i < P.out_cap; i += blockDim.x) {
         float* ob = P.out_boxes + ((size_t)b * P.out_cap + i) * 4;
