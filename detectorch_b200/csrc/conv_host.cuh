@@ -295,14 +295,6 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
         const int kb = p.ntaps * p.cin_blocks;
         L->slots = (bn <= 128 || (bn == 256 && (L->nmain != 0 || kb <= 16))) ? 2 : 1;
         if (force == 1 || force == 2) L->slots = force;
-        // pipeline depth actually used: the short-K layers are epilogue-bound and ran 7-9 % SLOWER with the 5-6 stages that fit since the
-        // in-place fp16 split (the producer runs several tiles ahead and competes with the epilogue's residual loads / stores for the
-        // TMA / L2 path); they cycle through DT_CONV_SHORTK_STAGES (default 3) of them
-        static int shortk = -1;
-        if (shortk < 0) { const char* e = getenv("DT_CONV_SHORTK_STAGES"); shortk = e ? atoi(e) : 3; }
-        static int aplanes_st = -1;
-        if (aplanes_st < 0) { const char* e = getenv("DT_CONV_APLANES_STAGES"); aplanes_st = e ? atoi(e) : 0; }
-        p.nstages = (bn == 256 && kb <= 8) ? shortk : ((p.a_planes && kb > 8) ? aplanes_st : 0);
     }
     return true;
 }
@@ -380,13 +372,6 @@ inline cudaError_t conv_launch_cfg(const ConvLayer& L, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-// residual prefetch ring of the short-K residual layers (conv3 of the bottlenecks): tiles in flight per epilogue group (DT_CONV_RING=2|3)
-inline int conv_ring_depth() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("DT_CONV_RING"); v = (e && e[0] == '3') ? 3 : 2; }
-    return v;
-}
-
 template <bool TWO, int KIND>
 inline cudaError_t conv_launch_sm(const ConvLayer& L, cudaStream_t stream) {
     // two staging slots only in the kind::f16 kernels (the engine default): the tf32 kind's stages are 64-96 KB
@@ -402,8 +387,10 @@ inline cudaError_t conv_launch_sm(const ConvLayer& L, cudaStream_t stream) {
             if (L.nmain == 0) {
                 if constexpr (TWO && KIND == KIND_F16X3) {
                     if (L.ring) {
+                        // residual prefetch ring: 2 tiles in flight per epilogue group with two staging slots (3 with one slot);
+                        // ring 3 + 2 slots (possible with 32 KB stages) measured 8-11 % slower than ring 2 + 2 slots
                         if (!s2) return conv_launch_cfg<256, 0, TWO, KIND, 3, 1>(L, stream);
-                        return conv_ring_depth() == 2 ? conv_launch_cfg<256, 0, TWO, KIND, 2, 2>(L, stream) : conv_launch_cfg<256, 0, TWO, KIND, 3, 2>(L, stream);
+                        return conv_launch_cfg<256, 0, TWO, KIND, 2, 2>(L, stream);
                     }
                     if (s2) return conv_launch_cfg<256, 0, TWO, KIND, 0, 2>(L, stream);
                 }

@@ -89,7 +89,6 @@ struct ConvParams {
     int out_planes;        // KIND_F16X3: write the output as a pair of fp16 planes (hi = fp16(y), lo = fp16(y - hi)) instead of fp32
     int* range_flag;       // KIND_F16X3: set to 1 when an activation does not fit fp16 (|x| >= 65504 or NaN); may be null
     int pdl;               // launched with programmatic stream serialization: release the next launch early, wait for the previous one
-    int nstages;           // pipeline stages actually cycled through (<= the stages that fit; 0 = all): short-K layers run best with 2-3
 };
 
 template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND, int RING = 0, int SLOTS = 1>
@@ -102,11 +101,16 @@ struct ConvCfg {
     static constexpr int B_ROW_BYTES = KIND == KIND_F16X3 ? 64 : 128; // 32 k-elements per row
     static constexpr int B_BYTES = (kTwoSM ? BLOCK_N / 2 : BLOCK_N) * B_ROW_BYTES;
     // tf32: A, A_lo (16 KB each), B_hi, B_lo.
-    // f16 : ONE 16 KB A area.  TMA delivers the fp32 tile into it; the converter warps read their rows into registers, meet at a named
-    //       barrier and write A_h | A_l (8 KB each) IN PLACE over the fp32 data (the two fp16 tiles are exactly as large as the fp32 tile);
-    //       with a_planes TMA delivers A_h | A_l there directly.  A stage is 32 KB instead of 48 KB: 5-6 pipeline stages instead of 3-4,
-    //       i.e. more bytes in flight for the layers that are bound by HBM latency x bandwidth, and room for two epilogue slots everywhere.
-    static constexpr int A_STAGE_BYTES = KIND == KIND_F16X3 ? A_BYTES : 2 * A_BYTES;
+    // f16 : A (fp32 staging, 16 KB), A_h | A_l (8 KB each), B_h, B_l -- or, INPLACE, ONE 16 KB A area: TMA delivers the fp32 tile into
+    //       it; the converter warps read their rows into registers, meet at a named barrier and write A_h | A_l IN PLACE over the fp32
+    //       data (the two fp16 tiles are exactly as large as the fp32 tile); with a_planes TMA delivers A_h | A_l there directly.  A stage
+    //       is then 32 KB instead of 48 KB (5-6 pipeline stages instead of 3-4).  Same-box A/B (profiles/r02_summary.md): the deeper
+    //       pipeline gives -4..7 % on the long-K 256-wide layers (mask K-split convs, conv1 of layers 3-4, P2/P3 3x3, FC6), but the
+    //       extra barrier / the serialised read-then-write make the conversion-bound 64-wide layers and the epilogue-bound short-K layers
+    //       4-7 % slower: in place only for the long-K instantiations (256 wide, no ring, NMAIN = 1 or one epilogue slot).
+    static constexpr bool INPLACE = KIND == KIND_F16X3 && BLOCK_N == 256 && RING == 0 && (NMAIN == 1 || SLOTS == 1);
+    static constexpr int A_STAGE_BYTES = INPLACE ? A_BYTES : 2 * A_BYTES;
+    static constexpr int A_OP_OFF = (KIND == KIND_F16X3 && !INPLACE) ? A_BYTES : 0;      // where A_h starts inside a stage (kind::f16)
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + 2 * B_BYTES;
     // epilogue staging: each of the two epilogue groups owns EPI_SLOTS 16 KB slots (128 rows x 32 channels).  With ONE slot the group's
     // per-chunk chain is  TMEM load -> scale/shift/residual -> staging -> TMA store -> wait until the store has READ the slot -> next chunk;
@@ -168,7 +172,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_kb = p.ntaps * p.cin_blocks;
-    const uint32_t nst = (p.nstages > 0 && p.nstages < STAGES) ? (uint32_t)p.nstages : (uint32_t)STAGES;
     const int num_items = p.m_pairs * p.n_tiles;
     const int pair = blockIdx.x >> 1;
     const int num_pairs = gridDim.x >> 1;
@@ -229,8 +232,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                 int w0, h0, n0img, n0;
                 tile_of(item, w0, h0, n0img, n0);
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = (int)(it % nst);
-                    const uint32_t ph = (it / nst) & 1u;
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(bar_empty(s), ph ^ 1u);
                     const int tap_l = kb / p.cin_blocks;
                     const int cb = kb - tap_l * p.cin_blocks;
@@ -241,8 +244,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                     mbar_arrive_expect_tx(bar_full(s), tx_bytes);
                     if (KIND == KIND_F16X3 && p.a_planes) {
                         // fp16 planes: the two operand tiles land where the converters would have written them
-                        tma_load_4d(st, &p.tm_a, bar_full(s), cb * 32, w0 * p.stride_w + fx - p.pad_w, h0 * p.stride_h + fy - p.pad_h, n0img);
-                        tma_load_4d(st + Cfg::A_BYTES / 2, &p.tm_a2, bar_full(s), cb * 32, w0 * p.stride_w + fx - p.pad_w,
+                        tma_load_4d(st + Cfg::A_OP_OFF, &p.tm_a, bar_full(s), cb * 32, w0 * p.stride_w + fx - p.pad_w, h0 * p.stride_h + fy - p.pad_h, n0img);
+                        tma_load_4d(st + Cfg::A_OP_OFF + Cfg::A_BYTES / 2, &p.tm_a2, bar_full(s), cb * 32, w0 * p.stride_w + fx - p.pad_w,
                                     h0 * p.stride_h + fy - p.pad_h, n0img);
                     } else {
                         tma_load_4d(st, &p.tm_a, bar_full(s), cb * 32, w0 * p.stride_w + fx - p.pad_w, h0 * p.stride_h + fy - p.pad_h, n0img);
@@ -285,8 +288,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
             tc_fence_after();
             const uint32_t acc0 = tmem_acc + (uint32_t)(buf * Cfg::TILE_COLS);
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                const int s = (int)(it % nst);
-                const uint32_t ph = (it / nst) & 1u;
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1u;
                 if constexpr (kTwoSM) mbar_wait_cluster(bar_conv(s), ph);   // both CTAs' TMA data landed and both converted A tiles are published
                 else mbar_wait(bar_conv(s), ph);      // converters waited on full[s] and published their tiles
                 tc_fence_after();
@@ -294,8 +297,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                     const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
                     uint64_t da, dal, dbh, dbl;      // "hi" A, "lo" A, "hi" B, "lo" B
                     if constexpr (KIND == KIND_F16X3) {
-                        da = umma_desc_k_sw64(st);
-                        dal = umma_desc_k_sw64(st + Cfg::A_BYTES / 2);
+                        da = umma_desc_k_sw64(st + Cfg::A_OP_OFF);
+                        dal = umma_desc_k_sw64(st + Cfg::A_OP_OFF + Cfg::A_BYTES / 2);
                         dbh = umma_desc_k_sw64(st + Cfg::A_STAGE_BYTES);
                         dbl = umma_desc_k_sw64(st + Cfg::A_STAGE_BYTES + Cfg::B_BYTES);
                     } else {
@@ -340,46 +343,79 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
         uint32_t it = 0;
         for (int item = pair; item < num_items; item += num_pairs) {
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                const int s = (int)(it % nst);
-                const uint32_t ph = (it / nst) & 1u;
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1u;
                 mbar_wait(bar_full(s), ph);
                 if (KIND == KIND_F16X3 && p.a_planes) {
                     // operand tiles were delivered by TMA (async proxy): nothing to convert, just pass the stage on
                 } else if constexpr (KIND == KIND_F16X3) {
-                    // A_h = fp16(A), A_l = fp16(A - A_h), IN PLACE: a thread owns one row -- 8 x 16-byte pieces of the 128B-swizzled fp32 row in
-                    // (registers), then, once every converter thread has read its row (named barrier: the fp16 tiles overlay other threads'
-                    // fp32 rows), 4 x 16-byte pieces of each 64B-swizzled fp16 row out (both access patterns are conflict-free)
-                    uint8_t* a32 = smem_gen + s * Cfg::STAGE_BYTES;
-                    uint8_t* ah = a32;
-                    uint8_t* al = ah + Cfg::A_BYTES / 2;
-                    bool bad = false;
-                    // rows past the TMA box (boxes smaller than 128 pixels) are never written: whatever they hold produces accumulator
-                    // rows that are never stored, but it must not trip the range flag
-                    const bool live_row = (ct & 127) * 128 < p.a_tile_bytes;
-                    static_assert(Cfg::CONV_THREADS == 128, "the in-place split maps one converter thread to one tile row");
-                    const int r = ct;
-                    float4 fin[8];
+                    if constexpr (Cfg::INPLACE) {
+                        // A_h = fp16(A), A_l = fp16(A - A_h), IN PLACE: a thread owns one row -- 8 x 16-byte pieces of the 128B-swizzled fp32 row in
+                        // (registers), then, once every converter thread has read its row (named barrier: the fp16 tiles overlay other threads'
+                        // fp32 rows), 4 x 16-byte pieces of each 64B-swizzled fp16 row out (both access patterns are conflict-free)
+                        uint8_t* a32 = smem_gen + s * Cfg::STAGE_BYTES;
+                        uint8_t* ah = a32;
+                        uint8_t* al = ah + Cfg::A_BYTES / 2;
+                        bool bad = false;
+                        // rows past the TMA box (boxes smaller than 128 pixels) are never written: whatever they hold produces accumulator
+                        // rows that are never stored, but it must not trip the range flag
+                        const bool live_row = (ct & 127) * 128 < p.a_tile_bytes;
+                        static_assert(Cfg::CONV_THREADS == 128, "the in-place split maps one converter thread to one tile row");
+                        const int r = ct;
+                        float4 fin[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) fin[i] = *reinterpret_cast<const float4*>(a32 + r * 128 + ((i ^ (r & 7)) << 4));
-                    named_bar_sync(3, Cfg::CONV_THREADS);          // ids 1, 2 belong to the epilogue groups
+                        for (int i = 0; i < 8; ++i) fin[i] = *reinterpret_cast<const float4*>(a32 + r * 128 + ((i ^ (r & 7)) << 4));
+                        named_bar_sync(3, Cfg::CONV_THREADS);          // ids 1, 2 belong to the epilogue groups
 #pragma unroll
-                    for (int c8 = 0; c8 < 4; ++c8) {
-                        const float4 v0 = fin[2 * c8], v1 = fin[2 * c8 + 1];
-                        const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                        __half2 hh[4], ll[4];
+                        for (int c8 = 0; c8 < 4; ++c8) {
+                            const float4 v0 = fin[2 * c8], v1 = fin[2 * c8 + 1];
+                            const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                            __half2 hh[4], ll[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const __half h0 = __float2half_rn(f[2 * j]), h1 = __float2half_rn(f[2 * j + 1]);
-                            bad = bad || !(fabsf(f[2 * j]) < 65504.f) || !(fabsf(f[2 * j + 1]) < 65504.f);
-                            hh[j] = __halves2half2(h0, h1);
-                            ll[j] = __halves2half2(__float2half_rn(f[2 * j] - __half2float(h0)), __float2half_rn(f[2 * j + 1] - __half2float(h1)));
+                            for (int j = 0; j < 4; ++j) {
+                                const __half h0 = __float2half_rn(f[2 * j]), h1 = __float2half_rn(f[2 * j + 1]);
+                                bad = bad || !(fabsf(f[2 * j]) < 65504.f) || !(fabsf(f[2 * j + 1]) < 65504.f);
+                                hh[j] = __halves2half2(h0, h1);
+                                ll[j] = __halves2half2(__float2half_rn(f[2 * j] - __half2float(h0)), __float2half_rn(f[2 * j + 1] - __half2float(h1)));
+                            }
+                            const int off = r * 64 + ((c8 ^ ((r >> 1) & 3)) << 4);
+                            *reinterpret_cast<uint4*>(ah + off) = *reinterpret_cast<const uint4*>(hh);
+                            if (p.passes == 3) *reinterpret_cast<uint4*>(al + off) = *reinterpret_cast<const uint4*>(ll);
                         }
-                        const int off = r * 64 + ((c8 ^ ((r >> 1) & 3)) << 4);
-                        *reinterpret_cast<uint4*>(ah + off) = *reinterpret_cast<const uint4*>(hh);
-                        if (p.passes == 3) *reinterpret_cast<uint4*>(al + off) = *reinterpret_cast<const uint4*>(ll);
+                        if (bad && live_row && p.range_flag) *p.range_flag = 1;
+                        fence_proxy_async_smem();
+                    } else {
+                        // A_h = fp16(A), A_l = fp16(A - A_h): thread -> (row, 8-channel group); two 16-byte pieces of the 128B-swizzled
+                        // fp32 row in, one 16-byte piece of each 64B-swizzled fp16 row out (both access patterns are conflict-free)
+                        const uint8_t* a32 = smem_gen + s * Cfg::STAGE_BYTES;
+                        uint8_t* ah = smem_gen + s * Cfg::STAGE_BYTES + Cfg::A_BYTES;
+                        uint8_t* al = ah + Cfg::A_BYTES / 2;
+                        bool bad = false;
+                        // rows past the TMA box (boxes smaller than 128 pixels) are never written: whatever they hold produces accumulator
+                        // rows that are never stored, but it must not trip the range flag
+                        const bool live_row = (ct & 127) * 128 < p.a_tile_bytes;
+                        constexpr int PIECES = 4 * 128 / Cfg::CONV_THREADS;        // 16-byte fp16 pieces per thread (4 or 2)
+#pragma unroll
+                        for (int i = 0; i < PIECES; ++i) {
+                            const int r = ct & 127, c8 = (ct >> 7) * PIECES + i;
+                            const float4 v0 = *reinterpret_cast<const float4*>(a32 + r * 128 + (((2 * c8) ^ (r & 7)) << 4));
+                            const float4 v1 = *reinterpret_cast<const float4*>(a32 + r * 128 + (((2 * c8 + 1) ^ (r & 7)) << 4));
+                            const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                            __half2 hh[4], ll[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const __half h0 = __float2half_rn(f[2 * j]), h1 = __float2half_rn(f[2 * j + 1]);
+                                bad = bad || !(fabsf(f[2 * j]) < 65504.f) || !(fabsf(f[2 * j + 1]) < 65504.f);
+                                hh[j] = __halves2half2(h0, h1);
+                                ll[j] = __halves2half2(__float2half_rn(f[2 * j] - __half2float(h0)), __float2half_rn(f[2 * j + 1] - __half2float(h1)));
+                            }
+                            const int off = r * 64 + ((c8 ^ ((r >> 1) & 3)) << 4);
+                            *reinterpret_cast<uint4*>(ah + off) = *reinterpret_cast<const uint4*>(hh);
+                            if (p.passes == 3) *reinterpret_cast<uint4*>(al + off) = *reinterpret_cast<const uint4*>(ll);
+                        }
+                        if (bad && live_row && p.range_flag) *p.range_flag = 1;
+                        fence_proxy_async_smem();
                     }
-                    if (bad && live_row && p.range_flag) *p.range_flag = 1;
-                    fence_proxy_async_smem();
                 } else if (p.passes == 3) {
                     // A_lo = A - trunc_tf32(A), element-wise, so the swizzled placement is preserved verbatim
                     const float4* a = reinterpret_cast<const float4*>(smem_gen + s * Cfg::STAGE_BYTES);

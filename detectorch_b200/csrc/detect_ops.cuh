@@ -823,6 +823,7 @@ static __global__ void __launch_bounds__(1024) det_limit_kernel(const __grid_con
     __syncthreads();
     for (int j = 1 + warp; j < P.NC; j += nwarps) {
         int c = 0;
+#pragma unroll 8
         for (int base = 0; base < P.R; base += 32) {
             const int ri = base + lane;
             c += __popc(__ballot_sync(0xffffffffu, ri < P.R && flag[(size_t)j * P.R + ri]));
@@ -835,7 +836,8 @@ static __global__ void __launch_bounds__(1024) det_limit_kernel(const __grid_con
         // image_thresh = np.sort(image_scores)[-max_dets]  == max_dets-th largest: gather the kept scores (class-major, RoI ascending), sort
         for (int j = 1 + warp; j < P.NC; j += nwarps) {
             int o = cls_off[j];
-            for (int base = 0; base < P.R; base += 32) {
+    #pragma unroll 8
+        for (int base = 0; base < P.R; base += 32) {
                 const int ri = base + lane;
                 const bool f = ri < P.R && flag[(size_t)j * P.R + ri];
                 const unsigned m = __ballot_sync(0xffffffffu, f);
@@ -860,7 +862,8 @@ static __global__ void __launch_bounds__(1024) det_limit_kernel(const __grid_con
         __syncthreads();
         for (int j = 1 + warp; j < P.NC; j += nwarps) {
             int c = 0;
-            for (int base = 0; base < P.R; base += 32) {
+    #pragma unroll 8
+        for (int base = 0; base < P.R; base += 32) {
                 const int ri = base + lane;
                 const bool f = ri < P.R && flag[(size_t)j * P.R + ri] && P.cls[((size_t)b * P.R + ri) * P.NC + j] >= thresh;
                 c += __popc(__ballot_sync(0xffffffffu, f));
@@ -872,6 +875,7 @@ static __global__ void __launch_bounds__(1024) det_limit_kernel(const __grid_con
     // emit in class-major / RoI-ascending order
     for (int j = 1 + warp; j < P.NC; j += nwarps) {
         int o = cls_off[j];
+#pragma unroll 8
         for (int base = 0; base < P.R; base += 32) {
             const int ri = base + lane;
             bool f = ri < P.R && flag[(size_t)j * P.R + ri];

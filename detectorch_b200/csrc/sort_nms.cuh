@@ -152,7 +152,8 @@ static __device__ int block_nms_sorted(const float4* boxes, int n, float thresh,
             if (lane == 0) sm->diag[i] = (unsigned long long)lo | ((unsigned long long)hi << 32);
         }
         __syncthreads();
-        // (b) serial resolve of this chunk
+        // (b) serial resolve of this chunk: one thread walks the survivors (the only truly sequential part of greedy NMS: a 64-bit mask and
+        // one dependent shared-memory read per kept box); the survivors' boxes are then compacted by 64 threads in parallel
         if (threadIdx.x == 0) {
             const unsigned long long valid = (cn == 64) ? ~0ull : ((1ull << cn) - 1ull);
             unsigned long long alive = ~removed[c] & valid, kept = 0ull;
@@ -161,8 +162,6 @@ static __device__ int block_nms_sorted(const float4* boxes, int n, float thresh,
                 const int b = __ffsll((long long)alive) - 1;
                 if (max_keep > 0 && tot >= max_keep) break;
                 kept |= 1ull << b;
-                sm->kbox[kc] = sm->cbox[b];
-                sm->karea[kc] = sm->carea[b];
                 ++kc; ++tot;
                 alive &= ~sm->diag[b];
                 alive &= ~(1ull << b);
@@ -170,6 +169,15 @@ static __device__ int block_nms_sorted(const float4* boxes, int n, float thresh,
             removed[c] = ~kept;
             sm->kcount = kc;
             sm->total_kept = tot;
+        }
+        __syncthreads();
+        if (threadIdx.x < 64) {
+            const unsigned long long kept = ~removed[c];
+            if ((kept >> threadIdx.x) & 1ull) {
+                const int pos = __popcll(kept & ((1ull << threadIdx.x) - 1ull));       // ascending order, as the serial walk produced it
+                sm->kbox[pos] = sm->cbox[threadIdx.x];
+                sm->karea[pos] = sm->carea[threadIdx.x];
+            }
         }
         __syncthreads();
         const int kc = sm->kcount;
