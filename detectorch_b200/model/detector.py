@@ -159,6 +159,7 @@ class detector(torch.nn.Module):
         # Engine options of the mirror: full [D,81,M,M] masks are what model.mask_head returns (reference layout); a caller that only uses the
         # fused detect() path may switch them off and size the padded detection slots (bench.py does)
         self.engine_defaults = dict(emit_full_masks=True, det_cap=128)
+        self.capture_graphs = os.environ.get("DT_DETECT_GRAPH", "1") != "0"      # detect(host batch): replay a captured CUDA graph of the step
         self._engines = collections.OrderedDict()      # LRU: (batch, h, w, overrides) -> (Engine, weights_version)
         self.max_cached_engines = int(os.environ.get("DT_ENGINE_CACHE", "6"))
         self._weights_version = 0
@@ -379,13 +380,28 @@ class detector(torch.nn.Module):
         eng.last_scaling_factor = float(scaling_factor)
         eng.set_original_size(0, 0)          # clip to the network input / scaling_factor (a previous postprocess_output may have set an image size)
         with_masks = self.use_mask_head if with_masks is None else with_masks
+        last = ST_MASK_OUT if with_masks else ST_DETECT
         if not images.is_cuda:
             images = self._upload(eng, images)
-        eng.run(images.contiguous().float(), float(scaling_factor), ST_TRUNK, ST_MASK_OUT if with_masks else ST_DETECT)
-        st = getattr(eng, "_stage_state", None)
-        if st is not None and st["pending"] is not None:
+            st = eng._stage_state
+            # host input = fixed device staging buffers: the ~110 launches of the step are captured once per (buffer, scaling factor, stage
+            # range) in a CUDA graph (second call on; the first one runs eagerly and warms every kernel up) and replayed afterwards
+            key = (st["pending"], float(scaling_factor), last)
+            g = st["graphs"].get(key)
+            if g is None and st["seen"].get(key, 0) >= 1 and self.capture_graphs:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    eng.run(images, float(scaling_factor), ST_TRUNK, last)
+                st["graphs"][key] = g
+            st["seen"][key] = st["seen"].get(key, 0) + 1
+            if g is not None:
+                g.replay()
+            else:
+                eng.run(images, float(scaling_factor), ST_TRUNK, last)
             st["free"][st["pending"]].record(torch.cuda.current_stream(eng.device))     # the staging buffer may be overwritten after this run
             st["pending"] = None
+        else:
+            eng.run(images.contiguous().float(), float(scaling_factor), ST_TRUNK, last)
         B, cap = images.size(0), eng.cfg.det_cap
         # "range_flag" (int32 [1]) is non-zero if an activation left the fp16 range of the default kind::f16 convolutions: read it together
         # with the results (no extra synchronisation here), or call engine_owning(out['boxes']).check_range()
@@ -403,7 +419,7 @@ class detector(torch.nn.Module):
             with torch.cuda.device(eng.device):
                 st = {"buf": [torch.empty((eng.cfg.batch, 3, eng.cfg.height, eng.cfg.width), dtype=torch.float32, device=eng.device) for _ in range(2)],
                       "up": [torch.cuda.Event() for _ in range(2)], "free": [torch.cuda.Event() for _ in range(2)],
-                      "stream": torch.cuda.Stream(device=eng.device), "i": 0, "pending": None}
+                      "stream": torch.cuda.Stream(device=eng.device), "i": 0, "pending": None, "graphs": {}, "seen": {}}
             eng._stage_state = st
         b = st["i"] % 2
         st["i"] += 1
