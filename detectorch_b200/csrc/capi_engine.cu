@@ -395,6 +395,7 @@ void plan_buffers(Engine* e) {
         add_buf(e, "rpn_cand", {B, L, pre, 4}); add_buf(e, "rpn_cand_score", {B, L, pre});
         add_buf(e, "rpn_order", {B, L, pre}, 1);
         add_buf(e, "rpn_sel_hist", {B, L, 2, 2048}, 1); add_buf(e, "rpn_sel_cc", {B, L, kRpnMaxChunks}, 1); add_buf(e, "rpn_sel_info", {B, L, 4}, 1);
+        add_buf(e, "rpn_cand_counts", {B, L}, 1); add_buf(e, "rpn_nms_mask", {B, L, pre, (pre + 63) / 64, 2}, 1);
         add_buf(e, "props", {B, L, post, 4}); add_buf(e, "prop_scores", {B, L, post}); add_buf(e, "prop_counts", {B, L}, 1);
         add_buf(e, "col_k0", {B, L * post}, 1); add_buf(e, "col_k1", {B, L * post}, 1);
         add_buf(e, "col_v0", {B, L * post}, 1); add_buf(e, "col_v1", {B, L * post}, 1);
@@ -538,7 +539,15 @@ cudaError_t launch_proposals(Engine* e, cudaStream_t s, int levels) {
         rpn_select_count_kernel<<<grid, 1024, 0, s>>>(P);
         rpn_select_scatter_kernel<<<grid, 1024, 0, s>>>(P);
     }
+    static int nms_split = -1;
+    if (nms_split < 0) { const char* v = getenv("DT_RPN_NMS_SPLIT"); nms_split = (v && v[0] == '0') ? 0 : 1; }
+    P.nms_split = (nms_split && P.pre_nms <= 8192 && P.nms_thresh > 0.f) ? 1 : 0;
     rpn_proposals_kernel<<<dim3(levels, e->cfg.batch), 1024, 0, s>>>(P);
+    if (P.nms_split) {
+        // DT_RPN_NMS_SPLIT=0 keeps the NMS inside rpn_proposals_kernel (one CTA per (level, image) sweeping every candidate over the survivors)
+        rpn_nms_mask_kernel<<<dim3(P.nms_chunks, P.nms_chunks, levels * e->cfg.batch), 64, 0, s>>>(P);
+        rpn_nms_scan_kernel<<<dim3(levels, e->cfg.batch), 1024, 0, s>>>(P);
+    }
     return cudaGetLastError();
 }
 cudaError_t fn_proposals(Engine* e, cudaStream_t s) { return launch_proposals(e, s, 5); }
@@ -724,6 +733,7 @@ bool build_program(Engine* e, std::map<std::string, ConvW>* cw) {
         P.out_props = e->buf("props"); P.out_scores = e->buf("prop_scores"); P.out_counts = e->buf<int>("prop_counts");
         P.dbg_order = e->buf<int>("rpn_order");
         P.sel_hist = e->buf<uint32_t>("rpn_sel_hist"); P.sel_chunk_counts = e->buf<int>("rpn_sel_cc"); P.sel_info = e->buf<int>("rpn_sel_info");
+        P.cand_counts = e->buf<int>("rpn_cand_counts"); P.nms_mask = e->buf<unsigned long long>("rpn_nms_mask"); P.nms_chunks = (c.pre_nms_top_n + 63) / 64;
         pb.fn(ST_PROPOSALS, fn_proposals);
         CollectParams& C = e->col;
         memset(&C, 0, sizeof(C));
@@ -1036,7 +1046,7 @@ int dt_engine_count_launches(dt_engine_t h, int first_stage, int last_stage) {
     int n = 0;
     for (const Op& op : e->ops)
         if (op.stage >= first_stage && op.stage <= last_stage)
-            n += (op.kind == 1 && e->fns[op.fn] == fn_detect) ? 2 : ((op.kind == 1 && op.stage == ST_PROPOSALS) ? (e->rpn.split ? 5 : 1) : 1);
+            n += (op.kind == 1 && e->fns[op.fn] == fn_detect) ? 2 : ((op.kind == 1 && op.stage == ST_PROPOSALS) ? ((e->rpn.split ? 5 : 1) + (e->rpn.nms_split ? 2 : 0)) : 1);
     return n;
 }
 

@@ -215,6 +215,11 @@ struct RpnParams {
     int* sel_chunk_counts;   // [B, L, kRpnMaxChunks]
     int* sel_info;           // [B, L, 4]: b1, b2, total (-1: not narrowed -> full sort), unused
     int split;               // 1: selection done by the multi-CTA kernels, rpn_proposals_kernel only finishes
+    // NMS at full-GPU width (rpn_nms_mask_kernel + rpn_nms_scan_kernel): rpn_proposals_kernel then stops after decode / filter
+    int nms_split;
+    int nms_chunks;          // ceil(pre_nms / 64)
+    int* cand_counts;        // [B, L] candidates that passed the filter
+    unsigned long long* nms_mask;   // [B, L, pre_nms, nms_chunks]: bit b of word (i, w) set <=> candidate i suppresses candidate w*64 + b (> i)
 };
 static constexpr int kRpnChunk = 4096;        // anchors per CTA of the selection kernels (1024 threads x 4)
 static constexpr int kRpnMaxChunks = 64;      // >= ceil(largest level / kRpnChunk): 182 400 / 4096 = 45 at 800x1216; levels above this use the one-CTA path
@@ -585,6 +590,12 @@ static __global__ void __launch_bounds__(1024) rpn_proposals_kernel(const __grid
         nc += tot;
     }
     __syncthreads();
+    if (P.nms_split && P.nms_thresh > 0.f) {
+        // the greedy NMS of the <= pre_nms candidates continues in rpn_nms_mask_kernel (all pair tests, every SM) and
+        // rpn_nms_scan_kernel (the sequential survivor walk): in this CTA the per-box sweep over the survivors was 45 % of the kernel
+        if (threadIdx.x == 0) P.cand_counts[b * P.num_levels + l] = nc;
+        return;
+    }
     // 4. NMS (:114-120); candidates are already in descending-score order
     float* op = P.out_props + ((size_t)b * P.num_levels + l) * P.post_nms * 4;
     float* os = P.out_scores + ((size_t)b * P.num_levels + l) * P.post_nms;
@@ -623,6 +634,104 @@ static __global__ void __launch_bounds__(1024) rpn_proposals_kernel(const __grid
         }
     }
     if (threadIdx.x == 0) P.out_counts[b * P.num_levels + l] = nout;
+}
+
+// ---- RPN NMS, part 1: the suppression bit-matrix of every (level, image), at full-GPU width.
+// grid (chunks, chunks, L*B), 64 threads: block (bj, bi) with bj >= bi fills word (i, bj) for the 64 candidates i of chunk bi:
+// bit b set <=> candidate i suppresses candidate bj*64 + b (only later candidates; cython_nms.pyx:76-85 semantics, iou_suppresses)
+static __global__ void __launch_bounds__(64) rpn_nms_mask_kernel(const __grid_constant__ RpnParams P) {
+    const int bj = blockIdx.x, bi = blockIdx.y, lb = blockIdx.z;      // lb = b * L + l
+    if (bj < bi) return;
+    const int n = P.cand_counts[lb];
+    if (bi * 64 >= n || bj * 64 >= n) return;
+    __shared__ float4 jb[64];
+    __shared__ float ja[64];
+    const float4* boxes = P.cand + (size_t)lb * P.pre_nms;
+    const int j0 = bj * 64, i = bi * 64 + threadIdx.x;
+    const int jn = min(64, n - j0);
+    if ((int)threadIdx.x < jn) { const float4 bx = boxes[j0 + threadIdx.x]; jb[threadIdx.x] = bx; ja[threadIdx.x] = box_area_p1(bx); }
+    __syncthreads();
+    if (i >= n) return;
+    const float4 me = boxes[i];
+    const float ma = box_area_p1(me);
+    unsigned long long bits = 0ull;
+    for (int t = 0; t < jn; ++t)
+        if (j0 + t > i && iou_suppresses(me, ma, jb[t], ja[t], P.nms_thresh)) bits |= 1ull << t;
+    P.nms_mask[((size_t)lb * P.pre_nms + i) * P.nms_chunks + bj] = bits;
+}
+
+// ---- RPN NMS, part 2: the sequential survivor walk over the bit-matrix + the first post_nms survivors out (generate_proposals.py:114-120).
+// grid (L, B), 1024 threads.
+static __global__ void __launch_bounds__(1024) rpn_nms_scan_kernel(const __grid_constant__ RpnParams P) {
+    __shared__ unsigned long long removed[128];   // up to 8192 candidates
+    __shared__ unsigned long long diag[64];
+    __shared__ int kept_list[64];
+    __shared__ int kcount, total_kept;
+    __shared__ int scratch[33];
+    const int l = blockIdx.x, b = blockIdx.y, lb = b * P.num_levels + l;
+    const int n = P.cand_counts[lb];
+    const int nchunks = (n + 63) >> 6, NCH = P.nms_chunks;
+    const unsigned long long* mask = P.nms_mask + (size_t)lb * P.pre_nms * NCH;
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) removed[i] = 0ull;
+    if (threadIdx.x == 0) total_kept = 0;
+    __syncthreads();
+    for (int c = 0; c < nchunks; ++c) {
+        const int cn = min(64, n - c * 64);
+        if ((int)threadIdx.x < cn) diag[threadIdx.x] = mask[(size_t)(c * 64 + threadIdx.x) * NCH + c];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long valid = (cn == 64) ? ~0ull : ((1ull << cn) - 1ull);
+            unsigned long long alive = ~removed[c] & valid, kept = 0ull;
+            int kc = 0, tot = total_kept;
+            while (alive) {
+                const int t = __ffsll((long long)alive) - 1;
+                if (P.post_nms > 0 && tot >= P.post_nms) break;
+                kept |= 1ull << t;
+                kept_list[kc++] = c * 64 + t;
+                ++tot;
+                alive &= ~diag[t];
+                alive &= ~(1ull << t);
+            }
+            removed[c] = ~kept;
+            kcount = kc;
+            total_kept = tot;
+        }
+        __syncthreads();
+        if (P.post_nms > 0 && total_kept >= P.post_nms) {
+            for (int i = c + 1 + threadIdx.x; i < nchunks; i += blockDim.x) removed[i] = ~0ull;
+            __syncthreads();
+            break;
+        }
+        // the survivors of this chunk suppress later candidates: OR their matrix rows into `removed`, one (survivor, word) pair per thread
+        const int kc = kcount, words = nchunks - c - 1;
+        for (int p = threadIdx.x; p < kc * words; p += blockDim.x) {
+            const int k = p / words, wd = c + 1 + (p - k * words);
+            const unsigned long long v = mask[(size_t)kept_list[k] * NCH + wd];
+            if (v) atomicOr(&removed[wd], v);
+        }
+        __syncthreads();
+    }
+    // ordered compaction of the survivors
+    const float4* cand = P.cand + (size_t)lb * P.pre_nms;
+    const float* cscore = P.cand_score + (size_t)lb * P.pre_nms;
+    float* op = P.out_props + (size_t)lb * P.post_nms * 4;
+    float* os = P.out_scores + (size_t)lb * P.post_nms;
+    int nout = 0;
+    for (int base_i = 0; base_i < n; base_i += blockDim.x) {
+        const int i = base_i + threadIdx.x;
+        const bool keep = (i < n) && !((removed[i >> 6] >> (i & 63)) & 1ull);
+        int tot;
+        const int r = block_rank(keep, scratch, &tot);
+        const int pos = nout + r;
+        if (keep && (P.post_nms <= 0 || pos < P.post_nms)) {
+            const float4 bx = cand[i];
+            op[pos * 4 + 0] = bx.x; op[pos * 4 + 1] = bx.y; op[pos * 4 + 2] = bx.z; op[pos * 4 + 3] = bx.w;
+            os[pos] = cscore[i];
+        }
+        nout += tot;
+    }
+    if (P.post_nms > 0 && nout > P.post_nms) nout = P.post_nms;
+    if (threadIdx.x == 0) P.out_counts[lb] = nout;
 }
 
 // ---------------------------------------------------------------------------------- collect + distribute
