@@ -227,6 +227,18 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
     d |= (uint64_t)4 << 61;
     return d;
 }
+// same with an explicit stride between 8-row groups.  The tensor core applies the swizzle to ABSOLUTE shared-memory addresses (probe:
+// tests/umma_shift_probe.cu -- any start row and SBO = 576 / 640 B give exact results with base_offset 0), so a start address shifted by
+// whole rows and an SBO that is not a multiple of the 512-byte atom address a sub-window of a larger TMA box (halo tile of a 3x3 conv).
+__device__ __forceinline__ uint64_t umma_desc_k_sw64_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
 // Instruction descriptor for kind::tf32 / kind::f16 with fp32 accumulate, K-major A and B
 //   [4,6) c_format=1(F32) | [7,10) a_format | [10,13) b_format | [17,23) N>>3 | [24,29) M>>4
 __host__ __device__ constexpr uint32_t umma_idesc2(int afmt, int bfmt /*0=f16,1=bf16,2=tf32*/, int M, int N) {

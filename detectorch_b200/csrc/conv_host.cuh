@@ -114,6 +114,7 @@ struct ConvLayer {
     int kind = KIND_TF32X3;
     int ring = 0;       // residual prefetch ring (short-K RES_TILE layers)
     int slots = 1;      // epilogue staging slots per group (2 = the TMA store of a chunk drains while the next chunk is computed)
+    bool halo = false;  // 3x3 halo variant: one (8 + 2)-pixel-wide A box per filter row serves its three taps
     dim3 grid;
     bool valid = false;
 };
@@ -182,6 +183,13 @@ inline bool conv_merge_acc(int num_kb) {
     return num_kb <= thr;
 }
 
+// DT_CONV_HALO=0 switches the halo variant of the 64 / 128-wide 3x3 plane-input layers off (A/B, tests)
+inline bool conv_use_halo() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DT_CONV_HALO"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
 // Persistent launch geometry: work items = (pairs of M-tiles) x (N-tiles); one 2-CTA cluster per SM pair (74 on B200),
 // each looping over items pair, pair + num_pairs, ...  An odd M-tile count gets one all-out-of-range surplus tile (TMA
 // zero-fills its loads and clips its stores) so that both CTAs of a pair always run the same multicast protocol.
@@ -211,13 +219,29 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
     int bn = s.force_block_n;
     if (bn == 0) bn = s.Cout > 128 ? 256 : (s.Cout > 64 ? 128 : 64);
     L->block_n = bn;
+    // Halo variant (conv_tcgen05.cuh): 3x3 / stride 1 / pad 1 over fp16 planes, tiles up to 128 channels wide in the two instantiations
+    // the engine uses for them (64: 1-SM MMA, 3 rotating accumulators; 128: 2-SM MMA, 1 accumulator).  Tiles are 8 pixels wide and
+    // (hbox x nbox) = 16 rows high; the A box is 10 pixels wide.
+    L->halo = conv_use_halo() && s.x_lo && s.kind == KIND_F16X3 && s.kh == 3 && s.kw == 3 && s.stride == 1 && s.pad == 1 && s.ntaps == 0 &&
+              s.passes != 1 && s.W >= 10 && ((bn == 64 && !conv_use_two_sm(64, 0)) || (bn == 128 && conv_use_two_sm(128, 0) && !s.precise));
+    if (L->halo) {
+        long best = -1;
+        for (int h = 16; h >= 1; h >>= 1) {
+            const int n = 16 / h;
+            if (h > s.H || n > s.N) continue;
+            const long tiles = (long)ceil_div(Wo, 8) * ceil_div(Ho, h) * ceil_div(s.N, n);
+            if (best < 0 || tiles < best) { best = tiles; hbox = h; nbox = n; }
+        }
+        if (best < 0) L->halo = false; else wbox = 8;
+    }
+    const int abox_w = L->halo ? wbox + 2 : wbox * s.stride;
     const int K = s.kh * s.kw * s.Cin;
     const uint64_t xs = (uint64_t)s.x_pix_stride * 4;
     if (s.x_lo) {
         if (s.kind != KIND_F16X3 || s.x_pix_stride != s.Cin) { fprintf(stderr, "[detectorch_b200] conv_build: fp16 input planes need the f16 kind and a dense layout\n"); return false; }
         const uint64_t hs = (uint64_t)s.Cin * 2;
-        if (!make_tmap_4d_f16(&p.tm_a, s.x, s.Cin, s.W, s.H, s.N, hs, hs * s.W, hs * s.W * s.H, 32, wbox * s.stride, hbox * s.stride, nbox, s.stride, s.stride) ||
-            !make_tmap_4d_f16(&p.tm_a2, s.x_lo, s.Cin, s.W, s.H, s.N, hs, hs * s.W, hs * s.W * s.H, 32, wbox * s.stride, hbox * s.stride, nbox, s.stride, s.stride))
+        if (!make_tmap_4d_f16(&p.tm_a, s.x, s.Cin, s.W, s.H, s.N, hs, hs * s.W, hs * s.W * s.H, 32, abox_w, hbox * s.stride, nbox, s.stride, s.stride) ||
+            !make_tmap_4d_f16(&p.tm_a2, s.x_lo, s.Cin, s.W, s.H, s.N, hs, hs * s.W, hs * s.W * s.H, 32, abox_w, hbox * s.stride, nbox, s.stride, s.stride))
             return false;
         p.a_planes = 1;
     } else if (!make_tmap_4d(&p.tm_a, s.x, s.Cin, s.W, s.H, s.N, xs, xs * s.W, xs * s.W * s.H, 32, wbox * s.stride, hbox * s.stride, nbox,
@@ -268,6 +292,7 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
     p.wo = Wo; p.ho = Ho; p.nimg = s.N;
     p.cout = s.Cout;
     p.a_tile_bytes = wbox * hbox * nbox * 128;
+    p.a_halo_bytes = L->halo ? (wbox + 2) * hbox * nbox * 64 : 0;
     p.relu = s.relu; p.sigmoid_ch = s.sigmoid_ch; p.res_mode = s.res_mode;
     p.passes = s.passes == 1 ? 1 : 3;
     // 256-wide tiles: (main + cross) accumulators fill the 512 TMEM columns, so the epilogue cannot overlap the next tile's MMAs.  One
@@ -295,6 +320,11 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
         const int kb = p.ntaps * p.cin_blocks;
         L->slots = (bn <= 128 || (bn == 256 && (L->nmain != 0 || kb <= 16))) ? 2 : 1;
         if (force == 1 || force == 2) L->slots = force;
+        if (L->halo) L->slots = 2;
+    }
+    if (L->halo && (L->nmain != (bn == 64 ? 3 : 1) || L->two_sm != (bn == 128) || L->ring)) {
+        fprintf(stderr, "[detectorch_b200] conv_build: halo layer ended up in an instantiation the halo kernel does not cover\n");
+        return false;
     }
     return true;
 }
@@ -347,12 +377,12 @@ inline bool conv_use_pdl() {
     return v == 1;
 }
 
-template <int BN, int NM, bool TWO, int KIND, int RING = 0, int SLOTS = 1>
+template <int BN, int NM, bool TWO, int KIND, int RING = 0, int SLOTS = 1, bool HALO = false>
 inline cudaError_t conv_launch_cfg(const ConvLayer& L, cudaStream_t stream) {
-    using Cfg = ConvCfg<BN, NM, TWO, KIND, RING, SLOTS>;
+    using Cfg = ConvCfg<BN, NM, TWO, KIND, RING, SLOTS, HALO>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel<BN, NM, TWO, KIND, RING, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel<BN, NM, TWO, KIND, RING, SLOTS, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -366,9 +396,9 @@ inline cudaError_t conv_launch_cfg(const ConvLayer& L, cudaStream_t stream) {
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel<BN, NM, TWO, KIND, RING, SLOTS>, prm);
+        return cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel<BN, NM, TWO, KIND, RING, SLOTS, HALO>, prm);
     }
-    conv_tcgen05_kernel<BN, NM, TWO, KIND, RING, SLOTS><<<L.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(L.p);
+    conv_tcgen05_kernel<BN, NM, TWO, KIND, RING, SLOTS, HALO><<<L.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(L.p);
     return cudaGetLastError();
 }
 
@@ -378,6 +408,13 @@ inline cudaError_t conv_launch_sm(const ConvLayer& L, cudaStream_t stream) {
     constexpr bool kCan2 = KIND == KIND_F16X3;
     const bool s2 = kCan2 && L.slots == 2;
     constexpr int S2 = kCan2 ? 2 : 1;
+    if constexpr (KIND == KIND_F16X3) {
+        if (L.halo) {
+            if constexpr (TWO) { if (L.block_n == 128) return conv_launch_cfg<128, 1, true, KIND_F16X3, 0, 2, true>(L, stream); }
+            else { if (L.block_n == 64) return conv_launch_cfg<64, 3, false, KIND_F16X3, 0, 2, true>(L, stream); }
+            return cudaErrorInvalidValue;
+        }
+    }
     switch (L.block_n) {
         case 64: return s2 ? conv_launch_cfg<64, 3, TWO, KIND, 0, S2>(L, stream) : conv_launch_cfg<64, 3, TWO, KIND, 0, 1>(L, stream);
         case 128:

@@ -89,9 +89,14 @@ struct ConvParams {
     int out_planes;        // KIND_F16X3: write the output as a pair of fp16 planes (hi = fp16(y), lo = fp16(y - hi)) instead of fp32
     int* range_flag;       // KIND_F16X3: set to 1 when an activation does not fit fp16 (|x| >= 65504 or NaN); may be null
     int pdl;               // launched with programmatic stream serialization: release the next launch early, wait for the previous one
+    int a_halo_bytes;      // HALO variant: bytes of ONE fp16 plane of the (wbox + 2) x hbox x nbox halo box (rows of 64 B)
 };
 
-template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND, int RING = 0, int SLOTS = 1>
+// HALO (3x3, stride 1, fp16-plane input, tiles 8 pixels wide): one TMA box of (8 + 2) x hbox x nbox pixels per (filter row, 32-channel
+// block) serves the THREE horizontal taps -- the A descriptor of tap dx starts dx rows into the box and steps 10 rows (640 B) from one
+// 8-pixel group to the next -- so the A tile is fetched from L2 3 times per tile instead of 9 (the 64/128-channel 3x3 layers were bound by
+// exactly that re-fetch: ncu 7.8 TB/s L2->SM at 23 % tensor-pipe activity).  A stage holds the halo planes + the weights of 3 taps.
+template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND, int RING = 0, int SLOTS = 1, bool HALO = false>
 struct ConvCfg {
     static constexpr int BLOCK_M = 128;
     static constexpr int BLOCK_K = 32;
@@ -109,9 +114,14 @@ struct ConvCfg {
     //       extra barrier / the serialised read-then-write make the conversion-bound 64-wide layers and the epilogue-bound short-K layers
     //       4-7 % slower: in place only for the long-K instantiations (256 wide, no ring, NMAIN = 1 or one epilogue slot).
     static constexpr bool INPLACE = KIND == KIND_F16X3 && BLOCK_N == 256 && RING == 0 && (NMAIN == 1 || SLOTS == 1);
-    static constexpr int A_STAGE_BYTES = INPLACE ? A_BYTES : 2 * A_BYTES;
-    static constexpr int A_OP_OFF = (KIND == KIND_F16X3 && !INPLACE) ? A_BYTES : 0;      // where A_h starts inside a stage (kind::f16)
-    static constexpr int STAGE_BYTES = A_STAGE_BYTES + 2 * B_BYTES;
+    static_assert(!HALO || (KIND == KIND_F16X3 && RING == 0 && !INPLACE), "the halo variant is a kind::f16, plane-input, no-ring kernel");
+    static constexpr int HALO_ROWS = 160;                            // (8 + 2) x 16 pixel rows of 64 B per plane
+    static constexpr int HALO_PLANE_BYTES = HALO_ROWS * 64;          // 10 KB, a multiple of the 512-byte swizzle atom
+    static constexpr int B_TAPS = HALO ? 3 : 1;                      // weight tiles per stage
+    static constexpr int A_STAGE_BYTES = HALO ? 2 * HALO_PLANE_BYTES : (INPLACE ? A_BYTES : 2 * A_BYTES);
+    static constexpr int A_OP_OFF = (KIND == KIND_F16X3 && !INPLACE && !HALO) ? A_BYTES : 0;      // where A_h starts inside a stage (kind::f16)
+    static constexpr int A_LO_OFF = A_OP_OFF + (HALO ? HALO_PLANE_BYTES : A_BYTES / 2);          // ... and A_l
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + 2 * B_BYTES * B_TAPS;
     // epilogue staging: each of the two epilogue groups owns EPI_SLOTS 16 KB slots (128 rows x 32 channels).  With ONE slot the group's
     // per-chunk chain is  TMEM load -> scale/shift/residual -> staging -> TMA store -> wait until the store has READ the slot -> next chunk;
     // with TWO slots the store of chunk i drains while chunk i+1 is computed.  Measured per layer (profiles/r02_ab_epilogue_slots.md):
@@ -144,9 +154,9 @@ struct ConvCfg {
     static_assert(8 * (NUM_BARS + 1) <= 256, "barrier area");
 };
 
-template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND, int RING = 0, int SLOTS = 1>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NMAIN, kTwoSM, KIND, RING, SLOTS>::THREADS), 1) conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
-    using Cfg = ConvCfg<BLOCK_N, NMAIN, kTwoSM, KIND, RING, SLOTS>;
+template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND, int RING = 0, int SLOTS = 1, bool HALO = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NMAIN, kTwoSM, KIND, RING, SLOTS, HALO>::THREADS), 1) conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
+    using Cfg = ConvCfg<BLOCK_N, NMAIN, kTwoSM, KIND, RING, SLOTS, HALO>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int NBUF = Cfg::NBUF;
     extern __shared__ uint8_t smem_raw[];
@@ -171,7 +181,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_kb = p.ntaps * p.cin_blocks;
+    // pipeline steps per tile: one k-block (32 channels of one filter tap) -- or, HALO, one (filter row, 32-channel block) = 3 taps
+    const int num_kb = HALO ? p.kh * p.cin_blocks : p.ntaps * p.cin_blocks;
     const int num_items = p.m_pairs * p.n_tiles;
     const int pair = blockIdx.x >> 1;
     const int num_pairs = gridDim.x >> 1;
@@ -235,6 +246,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(bar_empty(s), ph ^ 1u);
+                    if constexpr (HALO) {
+                        // step = (filter row fy, channel block cb): the two halo planes + the hi / lo weights of the row's three taps
+                        const int fy = kb / p.cin_blocks;
+                        const int cb = kb - fy * p.cin_blocks;
+                        const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
+                        mbar_arrive_expect_tx(bar_full(s), 2u * (uint32_t)p.a_halo_bytes + 6u * Cfg::B_BYTES);
+                        tma_load_4d(st, &p.tm_a, bar_full(s), cb * 32, w0 - 1, h0 + fy - 1, n0img);
+                        tma_load_4d(st + Cfg::HALO_PLANE_BYTES, &p.tm_a2, bar_full(s), cb * 32, w0 - 1, h0 + fy - 1, n0img);
+                        const int nrow = n0 + (int)cta_rank * (BLOCK_N / 2);
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const int kbg = (fy * 3 + dx) * p.cin_blocks + cb;
+                            const uint32_t bh = st + Cfg::A_STAGE_BYTES + dx * 2 * Cfg::B_BYTES, bl = bh + Cfg::B_BYTES;
+                            if constexpr (kTwoSM) {
+                                tma_load_2d(bh, &p.tm_bhi, bar_full(s), kbg * 32, nrow);
+                                tma_load_2d(bl, &p.tm_blo, bar_full(s), kbg * 32, nrow);
+                            } else {
+                                const uint32_t half = cta_rank * (Cfg::B_BYTES / 2);
+                                tma_load_2d_mcast(bh + half, &p.tm_bhi, bar_full(s), kbg * 32, nrow, (uint16_t)3);
+                                tma_load_2d_mcast(bl + half, &p.tm_blo, bar_full(s), kbg * 32, nrow, (uint16_t)3);
+                            }
+                        }
+                        continue;
+                    }
                     const int tap_l = kb / p.cin_blocks;
                     const int cb = kb - tap_l * p.cin_blocks;
                     const int tap = p.tap0 + tap_l;
@@ -295,10 +330,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
+                    if constexpr (HALO) {
+                        // tap dx of this filter row reads the halo box from pixel column dx on: start + dx rows, 10 rows between 8-pixel groups
+                        constexpr int NM = NMAIN == 0 ? 1 : NMAIN;
+                        const uint32_t acc_x = acc0 + (uint32_t)(NMAIN * BLOCK_N);
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const uint64_t da = umma_desc_k_sw64_sbo(st + dx * 64, 640);
+                            const uint64_t dal = umma_desc_k_sw64_sbo(st + Cfg::HALO_PLANE_BYTES + dx * 64, 640);
+                            const uint64_t dbh = umma_desc_k_sw64(st + Cfg::A_STAGE_BYTES + dx * 2 * Cfg::B_BYTES);
+                            const uint64_t dbl = umma_desc_k_sw64(st + Cfg::A_STAGE_BYTES + dx * 2 * Cfg::B_BYTES + Cfg::B_BYTES);
+                            const int idx = kb * 3 + dx;       // the main term rotates over the accumulators by tap
+                            const uint32_t acc_main = acc0 + (uint32_t)((idx % NM) * BLOCK_N);
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; ++k) {
+                                const uint64_t koff = (uint64_t)(k * 32 >> 4);
+                                const uint32_t main_flag = NMAIN == 0 ? 1u : ((idx >= NMAIN || k != 0) ? 1u : 0u);
+                                mma(acc_x, dal + koff, dbh + koff, (idx | k) != 0);
+                                mma(acc_x, da + koff, dbl + koff, 1u);
+                                mma(acc_main, da + koff, dbh + koff, main_flag);
+                            }
+                        }
+                    } else {
                     uint64_t da, dal, dbh, dbl;      // "hi" A, "lo" A, "hi" B, "lo" B
                     if constexpr (KIND == KIND_F16X3) {
                         da = umma_desc_k_sw64(st + Cfg::A_OP_OFF);
-                        dal = umma_desc_k_sw64(st + Cfg::A_OP_OFF + Cfg::A_BYTES / 2);
+                        dal = umma_desc_k_sw64(st + Cfg::A_LO_OFF);
                         dbh = umma_desc_k_sw64(st + Cfg::A_STAGE_BYTES);
                         dbl = umma_desc_k_sw64(st + Cfg::A_STAGE_BYTES + Cfg::B_BYTES);
                     } else {
@@ -325,6 +382,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                             mma(acc_x, da + koff, dbl + koff, 1u);
                         }
                         mma(acc_main, da + koff, dbh + koff, main_flag);
+                    }
                     }
                     if constexpr (kTwoSM) {
                         umma_commit_2sm_mcast(bar_empty(s), (uint16_t)3);                        // frees this stage in both CTAs
@@ -489,7 +547,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
             int w0, h0, n0img, n0;
             tile_of(item, w0, h0, n0img, n0);
             const int buf = t % NBUF;
-            const int nacc = (num_kb < NMAIN ? num_kb : NMAIN);
+            const int nacc = HALO ? NMAIN : (num_kb < NMAIN ? num_kb : NMAIN);     // HALO: >= 3 taps per tile, NMAIN <= 3
             const int nlive = nlive_of(item);
             // pixel coordinates of this row (needed for the upsample operand)
             int pw_ = 0, ph_ = 0, pn_ = 0;
