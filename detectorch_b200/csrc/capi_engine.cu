@@ -509,11 +509,19 @@ cudaError_t fn_stem_pack(Engine* e, cudaStream_t s) {
     stem_pack_nhwc4_kernel<<<grid_for(n), 256, 0, s>>>(e->image, e->cfg.batch, e->cfg.height, e->cfg.width, e->Hp, e->Wp, e->buf("stem_x4"));
     return cudaGetLastError();
 }
+cudaError_t fn_stem_pack_planes(Engine* e, cudaStream_t s) {
+    const long long n = (long long)e->cfg.batch * e->Hp * e->Wp;
+    uint2* xh = reinterpret_cast<uint2*>(e->buf("stem_x4"));
+    stem_pack_nhwc4_planes_kernel<<<grid_for(n), 256, 0, s>>>(e->image, e->cfg.batch, e->cfg.height, e->cfg.width, e->Hp, e->Wp, xh, xh + n,
+                                                             e->buf<int>("range_flag"));
+    return cudaGetLastError();
+}
 cudaError_t fn_maxpool(Engine* e, cudaStream_t s) {
     const long long n = (long long)e->cfg.batch * e->H2 * e->W2 * 16;
     maxpool3x3s2_nhwc_kernel<<<grid_for(n), 256, 0, s>>>(e->buf("c1"), e->cfg.batch, e->H1, e->W1, 64, e->H2, e->W2, e->buf("pool"));
     return cudaGetLastError();
 }
+
 cudaError_t fn_p6(Engine* e, cudaStream_t s) {
     const long long n = (long long)e->cfg.batch * e->LH[4] * e->LW[4] * 64;
     subsample2_nhwc_kernel<<<grid_for(n), 256, 0, s>>>(e->buf("P5"), e->cfg.batch, e->LH[3], e->LW[3], 256, e->LH[4], e->LW[4], e->buf("P6"));
@@ -631,21 +639,26 @@ bool build_program(Engine* e, std::map<std::string, ConvW>* cw) {
         Op op;
         op.stage = ST_TRUNK; op.kind = 0; op.fn = -1;
         op.flops = 2.0 * (double)B * e->H1 * e->W1 * 64.0 * 147.0;
+        bool stem_planes = false;
         if (c.stem_im2col) {
             e->stem_fused = false;
         } else if (c.conv_kind == 0) {
             op.matrix = e->matrix_of(sw.w);
             op.scale_src = e->wvec(sw.scale); op.scale16 = e->scale16_arena() + e->scale16_used; op.scale_n = 64;
             e->scale16_used += 64;
+            // plane_handover >= 3: the packed image arrives as two fp16 planes (the stem's converter warps -- 7 k-blocks of fp32 -> fp16
+            // splits per 64-wide tile -- were what bounded it)
+            stem_planes = c.plane_handover >= 3 && (e->Wp % 2) == 0;
             e->stem_fused = conv_build_stem(e->buf("stem_x4"), B, e->Hp, e->Wp, e->H1, e->W1, e->whi16(sw.w + 64 * 160), e->wlo16(sw.w + 64 * 160),
-                                            op.scale16, e->wvec(sw.shift), e->buf("c1"), c.passes, &op.conv, KIND_F16X3, e->buf<int>("range_flag"));
+                                            op.scale16, e->wvec(sw.shift), e->buf("c1"), c.passes, &op.conv, KIND_F16X3, e->buf<int>("range_flag"),
+                                            stem_planes);
             if (!e->stem_fused) { op.scale16 = nullptr; op.scale_src = nullptr; }
         } else {
             e->stem_fused = conv_build_stem(e->buf("stem_x4"), B, e->Hp, e->Wp, e->H1, e->W1, e->wmat(sw.w + 64 * 160), e->wlo(sw.w + 64 * 160),
                                             e->wvec(sw.scale), e->wvec(sw.shift), e->buf("c1"), c.passes, &op.conv);
         }
         if (e->stem_fused) {
-            pb.fn(ST_TRUNK, fn_stem_pack);
+            pb.fn(ST_TRUNK, stem_planes ? fn_stem_pack_planes : fn_stem_pack);
             e->ops.push_back(op);
         } else {
             if (!c.stem_im2col) fprintf(stderr, "[detectorch_b200] engine: fused stem descriptor rejected, using the im2col stem\n");
@@ -653,6 +666,8 @@ bool build_program(Engine* e, std::map<std::string, ConvW>* cw) {
             pb.conv(ST_TRUNK, "stem", e->buf("stem_col"), 1, 1, B * e->H1 * e->W1, 160, e->buf("c1"), 64, 0, 1, true);
         }
     }
+    // (measured and rejected: the pooled map as fp16 planes too -- its consumers, conv1 and the downsample conv of the first bottleneck, did
+    // not get faster, the pool kernel got 19 us slower)
     pb.fn(ST_TRUNK, fn_maxpool);
     const float* x = e->buf("pool");
     int h = e->H2, w = e->W2, cin = 64;

@@ -114,7 +114,8 @@ struct ConvLayer {
     int kind = KIND_TF32X3;
     int ring = 0;       // residual prefetch ring (short-K RES_TILE layers)
     int slots = 1;      // epilogue staging slots per group (2 = the TMA store of a chunk drains while the next chunk is computed)
-    bool halo = false;  // 3x3 halo variant: one (8 + 2)-pixel-wide A box per filter row serves its three taps
+    bool ws = false;    // weight-stationary halo kernel (64-wide, one N tile): the whole weight matrix stays resident in shared memory
+    int halo = 0;       // 1 = 3x3 halo variant: one (8 + 2)-pixel-wide A box per filter row serves its three taps; 2 = stem row-parity halo
     dim3 grid;
     bool valid = false;
 };
@@ -190,6 +191,13 @@ inline bool conv_use_halo() {
     return v == 1;
 }
 
+// weight-stationary form of the 64-wide halo kernels: DT_CONV_WS=0 off, 1 (default) the stem only, 2 also the 64-channel 3x3 layers
+inline int conv_ws_mode() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DT_CONV_WS"); v = e ? atoi(e) : 1; }
+    return v;
+}
+
 // Persistent launch geometry: work items = (pairs of M-tiles) x (N-tiles); one 2-CTA cluster per SM pair (74 on B200),
 // each looping over items pair, pair + num_pairs, ...  An odd M-tile count gets one all-out-of-range surplus tile (TMA
 // zero-fills its loads and clips its stores) so that both CTAs of a pair always run the same multicast protocol.
@@ -232,7 +240,7 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
             const long tiles = (long)ceil_div(Wo, 8) * ceil_div(Ho, h) * ceil_div(s.N, n);
             if (best < 0 || tiles < best) { best = tiles; hbox = h; nbox = n; }
         }
-        if (best < 0) L->halo = false; else wbox = 8;
+        if (best < 0) L->halo = 0; else wbox = 8;
     }
     const int abox_w = L->halo ? wbox + 2 : wbox * s.stride;
     const int K = s.kh * s.kw * s.Cin;
@@ -322,7 +330,11 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
         if (force == 1 || force == 2) L->slots = force;
         if (L->halo) L->slots = 2;
     }
-    if (L->halo && (L->nmain != (bn == 64 ? 3 : 1) || L->two_sm != (bn == 128) || L->ring)) {
+    // weight-stationary form of the 64-wide 3x3 halo layer (one N tile, all 18 k-blocks resident, 2-SM MMA): measured a wash to +4 % slower
+    // than the streaming form (167 -> 175 us; the stem gains 17 %), so it is opt-in here (DT_CONV_WS=2)
+    L->ws = L->halo == 1 && bn == 64 && conv_ws_mode() == 2 && s.Cout <= 64 && s.kh * s.kw * p.cin_blocks <= 18;
+    if (L->ws) L->two_sm = true;
+    if (L->halo && (L->nmain != (bn == 64 ? 3 : 1) || L->two_sm != (bn == 128 || L->ws) || L->ring)) {
         fprintf(stderr, "[detectorch_b200] conv_build: halo layer ended up in an instantiation the halo kernel does not cover\n");
         return false;
     }
@@ -335,15 +347,32 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
 // (2 pixels) delivers, per ky, one 32-float K-block per output pixel straight into the swizzled A tile (last 4 floats
 // hit zero weights).  K = 7 x 32.  H uses elementStride 2.
 inline bool conv_build_stem(const float* x4, int B, int Hp, int Wp, int H1, int W1, const void* w_hi, const void* w_lo, const float* scale,
-                            const float* shift, float* y, int passes, ConvLayer* L, int kind = KIND_TF32X3, int* range_flag = nullptr) {
+                            const float* shift, float* y, int passes, ConvLayer* L, int kind = KIND_TF32X3, int* range_flag = nullptr,
+                            bool x4_planes = false) {
     memset(&L->p, 0, sizeof(ConvParams));
     ConvParams& p = L->p;
     int wbox, hbox, nbox;
     choose_box(W1, H1, B, 256, &wbox, &hbox, &nbox);
     const int bn = 64;
     L->block_n = bn;
+    L->halo = 0;
     const uint64_t row = (uint64_t)Wp * 16;
-    if (!make_tmap_4d(&p.tm_a, x4, 32, W1, Hp, B, 32, row, row * Hp, 32, wbox, hbox * 2, nbox, 1, 2)) return false;
+    if (x4_planes) {
+        // x4 holds two fp16 planes [B, Hp, Wp, 4] back to back (hi, lo): same overlapping-stride window, 16 bytes (2 pixels) per step
+        if (kind != KIND_F16X3 || (Wp & 1)) return false;
+        const __half* xh = reinterpret_cast<const __half*>(x4);
+        const __half* xl = xh + (size_t)B * Hp * Wp * 4;
+        const uint64_t rowh = (uint64_t)Wp * 8;
+        // row-parity halo (conv_tcgen05.cuh, HALO == 2): tiles of 8 x 16 pixels of one image, A boxes of 16 + 3 stride-2 row slabs
+        L->halo = (conv_use_halo() && H1 >= 16 && W1 >= 8 && !conv_use_two_sm(64, 0)) ? 2 : 0;
+        if (L->halo) { wbox = 8; hbox = 16; nbox = 1; }
+        const int abox_h = L->halo ? (hbox + 3) * 2 : hbox * 2;
+        if (!make_tmap_4d_f16(&p.tm_a, xh, 32, W1, Hp, B, 16, rowh, rowh * Hp, 32, wbox, abox_h, nbox, 1, 2) ||
+            !make_tmap_4d_f16(&p.tm_a2, xl, 32, W1, Hp, B, 16, rowh, rowh * Hp, 32, wbox, abox_h, nbox, 1, 2))
+            return false;
+        p.a_planes = 1;
+        p.a_halo_bytes = L->halo ? wbox * (hbox + 3) * 64 : 0;
+    } else if (!make_tmap_4d(&p.tm_a, x4, 32, W1, Hp, B, 32, row, row * Hp, 32, wbox, hbox * 2, nbox, 1, 2)) return false;
     if (kind == KIND_F16X3) {
         if (!make_tmap_2d_f16(&p.tm_bhi, w_hi, 224, 64, 224 * 2, 32, bn / 2)) return false;
         if (!make_tmap_2d_f16(&p.tm_blo, w_lo, 224, 64, 224 * 2, 32, bn / 2)) return false;
@@ -366,6 +395,8 @@ inline bool conv_build_stem(const float* x4, int B, int Hp, int Wp, int H1, int 
     L->nmain = 3;
     L->slots = 2;
     finish_grid(L, 1);
+    L->ws = L->halo == 2 && conv_ws_mode() >= 1;
+    if (L->ws) L->two_sm = true;
     return true;
 }
 
@@ -377,12 +408,12 @@ inline bool conv_use_pdl() {
     return v == 1;
 }
 
-template <int BN, int NM, bool TWO, int KIND, int RING = 0, int SLOTS = 1, bool HALO = false>
+template <int BN, int NM, bool TWO, int KIND, int RING = 0, int SLOTS = 1, int HALO = 0, bool WS = false>
 inline cudaError_t conv_launch_cfg(const ConvLayer& L, cudaStream_t stream) {
-    using Cfg = ConvCfg<BN, NM, TWO, KIND, RING, SLOTS, HALO>;
+    using Cfg = ConvCfg<BN, NM, TWO, KIND, RING, SLOTS, HALO, WS>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel<BN, NM, TWO, KIND, RING, SLOTS, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel<BN, NM, TWO, KIND, RING, SLOTS, HALO, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -396,9 +427,9 @@ inline cudaError_t conv_launch_cfg(const ConvLayer& L, cudaStream_t stream) {
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel<BN, NM, TWO, KIND, RING, SLOTS, HALO>, prm);
+        return cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel<BN, NM, TWO, KIND, RING, SLOTS, HALO, WS>, prm);
     }
-    conv_tcgen05_kernel<BN, NM, TWO, KIND, RING, SLOTS, HALO><<<L.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(L.p);
+    conv_tcgen05_kernel<BN, NM, TWO, KIND, RING, SLOTS, HALO, WS><<<L.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(L.p);
     return cudaGetLastError();
 }
 
@@ -410,8 +441,14 @@ inline cudaError_t conv_launch_sm(const ConvLayer& L, cudaStream_t stream) {
     constexpr int S2 = kCan2 ? 2 : 1;
     if constexpr (KIND == KIND_F16X3) {
         if (L.halo) {
-            if constexpr (TWO) { if (L.block_n == 128) return conv_launch_cfg<128, 1, true, KIND_F16X3, 0, 2, true>(L, stream); }
-            else { if (L.block_n == 64) return conv_launch_cfg<64, 3, false, KIND_F16X3, 0, 2, true>(L, stream); }
+            if constexpr (TWO) {
+                if (L.block_n == 128 && L.halo == 1) return conv_launch_cfg<128, 1, true, KIND_F16X3, 0, 2, 1>(L, stream);
+                if (L.block_n == 64 && L.halo == 1 && L.ws) return conv_launch_cfg<64, 3, true, KIND_F16X3, 0, 2, 1, true>(L, stream);
+                if (L.block_n == 64 && L.halo == 2 && L.ws) return conv_launch_cfg<64, 3, true, KIND_F16X3, 0, 2, 2, true>(L, stream);
+            } else {
+                if (L.block_n == 64 && L.halo == 1) return conv_launch_cfg<64, 3, false, KIND_F16X3, 0, 2, 1>(L, stream);
+                if (L.block_n == 64 && L.halo == 2) return conv_launch_cfg<64, 3, false, KIND_F16X3, 0, 2, 2>(L, stream);
+            }
             return cudaErrorInvalidValue;
         }
     }

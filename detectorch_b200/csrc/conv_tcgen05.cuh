@@ -96,7 +96,11 @@ struct ConvParams {
 // block) serves the THREE horizontal taps -- the A descriptor of tap dx starts dx rows into the box and steps 10 rows (640 B) from one
 // 8-pixel group to the next -- so the A tile is fetched from L2 3 times per tile instead of 9 (the 64/128-channel 3x3 layers were bound by
 // exactly that re-fetch: ncu 7.8 TB/s L2->SM at 23 % tensor-pipe activity).  A stage holds the halo planes + the weights of 3 taps.
-template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND, int RING = 0, int SLOTS = 1, bool HALO = false>
+// HALO == 2 (the 7-tap, stride-2 fused-window stem over fp16 planes, tiles 8 x 16 pixels of one image): a step is one PARITY of the filter
+// rows -- the even rows ky = 0, 2, 4, 6 read input rows 2 (h + j), j = 0..3, the odd rows ky = 1, 3, 5 input rows 2 (h + j) + 1 -- so one
+// stride-2 box of 16 + 3 row slabs serves the 4 (3) taps of a parity: tap j starts j slabs (j x 8 rows = j swizzle atoms) into the box.
+// The A tile is fetched 2 times per tile instead of 7.
+template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND, int RING = 0, int SLOTS = 1, int HALO = 0, bool WS = false>
 struct ConvCfg {
     static constexpr int BLOCK_M = 128;
     static constexpr int BLOCK_K = 32;
@@ -115,13 +119,19 @@ struct ConvCfg {
     //       4-7 % slower: in place only for the long-K instantiations (256 wide, no ring, NMAIN = 1 or one epilogue slot).
     static constexpr bool INPLACE = KIND == KIND_F16X3 && BLOCK_N == 256 && RING == 0 && (NMAIN == 1 || SLOTS == 1);
     static_assert(!HALO || (KIND == KIND_F16X3 && RING == 0 && !INPLACE), "the halo variant is a kind::f16, plane-input, no-ring kernel");
-    static constexpr int HALO_ROWS = 160;                            // (8 + 2) x 16 pixel rows of 64 B per plane
+    static constexpr int HALO_ROWS = 160;                            // (8 + 2) x 16 pixel rows of 64 B per plane (HALO == 2: 8 x (16 + 3) = 152)
     static constexpr int HALO_PLANE_BYTES = HALO_ROWS * 64;          // 10 KB, a multiple of the 512-byte swizzle atom
-    static constexpr int B_TAPS = HALO ? 3 : 1;                      // weight tiles per stage
+    static constexpr int B_TAPS = HALO == 1 ? 3 : (HALO == 2 ? 4 : 1);   // weight tiles per stage
     static constexpr int A_STAGE_BYTES = HALO ? 2 * HALO_PLANE_BYTES : (INPLACE ? A_BYTES : 2 * A_BYTES);
     static constexpr int A_OP_OFF = (KIND == KIND_F16X3 && !INPLACE && !HALO) ? A_BYTES : 0;      // where A_h starts inside a stage (kind::f16)
     static constexpr int A_LO_OFF = A_OP_OFF + (HALO ? HALO_PLANE_BYTES : A_BYTES / 2);          // ... and A_l
-    static constexpr int STAGE_BYTES = A_STAGE_BYTES + 2 * B_BYTES * B_TAPS;
+    // WS (weight-stationary; halo variants, 64-wide, one N tile, 2-SM MMA so that each CTA keeps only 32 weight rows): the hi / lo weights of
+    // ALL k-blocks are loaded once per CTA and stay resident; a stage then holds the A halo planes only.  After the halo cut the A
+    // re-fetch, the per-tile weight fetch was more than half of the L2 -> SM traffic of the 64-channel 3x3 layers and of the stem (ncu: 7.8 TB/s).
+    static_assert(!WS || (HALO != 0 && kTwoSM && BLOCK_N == 64), "weight-stationary: halo variants of the 64-wide 2-SM kernel only");
+    static constexpr int BRES_KB = WS ? (HALO == 1 ? 18 : 7) : 0;   // resident k-blocks: 3x3 x 64 channels, or the stem's 7 filter rows
+    static constexpr int BRES_BYTES = BRES_KB * 2 * B_BYTES;
+    static constexpr int STAGE_BYTES = WS ? A_STAGE_BYTES : A_STAGE_BYTES + 2 * B_BYTES * B_TAPS;
     // epilogue staging: each of the two epilogue groups owns EPI_SLOTS 16 KB slots (128 rows x 32 channels).  With ONE slot the group's
     // per-chunk chain is  TMEM load -> scale/shift/residual -> staging -> TMA store -> wait until the store has READ the slot -> next chunk;
     // with TWO slots the store of chunk i drains while chunk i+1 is computed.  Measured per layer (profiles/r02_ab_epilogue_slots.md):
@@ -134,14 +144,15 @@ struct ConvCfg {
     // (<= 16 k-blocks per tile) makes do with two pipeline stages.
     static constexpr int RING_BYTES = 2 * RING * A_BYTES;
     static constexpr int EPI_BYTES = 2 * EPI_SLOTS * A_BYTES;
-    static constexpr int STAGES_FIT = (196608 + 2 * A_BYTES - EPI_BYTES - RING_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES_FIT = (196608 + 2 * A_BYTES - EPI_BYTES - RING_BYTES - BRES_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
-    static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int BRES_OFF = STAGES * STAGE_BYTES;            // resident weights follow the pipeline stages
+    static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES + BRES_BYTES;
     static_assert(STAGES >= 2, "pipeline too shallow");
     static constexpr int TILE_COLS = (NMAIN + 1) * BLOCK_N;          // TMEM columns of one tile's accumulators
     static constexpr int NBUF = (2 * TILE_COLS <= 512) ? 2 : 1;      // double-buffer the accumulators when they fit
     static constexpr int TMEM_COLS = (NBUF * TILE_COLS > 256) ? 512 : (NBUF * TILE_COLS > 128 ? 256 : 128);
-    static constexpr int NUM_BARS = 3 * STAGES + 2 * NBUF + 2 * EPI_SLOTS + 2 * RING;
+    static constexpr int NUM_BARS = 3 * STAGES + 2 * NBUF + 2 * EPI_SLOTS + 2 * RING + (WS ? 1 : 0);
     static constexpr int SMEM_BYTES = PIPE_BYTES + EPI_BYTES + RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     // converter warps: the fp16 split of a 16 KB tile costs ~2x the tf32 residual and, for tiles up to 128 wide, more than the
     // MMAs of a k-block -> 8 warps there (two 16-byte pieces per thread), 4 otherwise
@@ -154,9 +165,9 @@ struct ConvCfg {
     static_assert(8 * (NUM_BARS + 1) <= 256, "barrier area");
 };
 
-template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND, int RING = 0, int SLOTS = 1, bool HALO = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NMAIN, kTwoSM, KIND, RING, SLOTS, HALO>::THREADS), 1) conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
-    using Cfg = ConvCfg<BLOCK_N, NMAIN, kTwoSM, KIND, RING, SLOTS, HALO>;
+template <int BLOCK_N, int NMAIN, bool kTwoSM, int KIND, int RING = 0, int SLOTS = 1, int HALO = 0, bool WS = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NMAIN, kTwoSM, KIND, RING, SLOTS, HALO, WS>::THREADS), 1) conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
+    using Cfg = ConvCfg<BLOCK_N, NMAIN, kTwoSM, KIND, RING, SLOTS, HALO, WS>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int NBUF = Cfg::NBUF;
     extern __shared__ uint8_t smem_raw[];
@@ -176,13 +187,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
     auto bar_tempty = [&](int b) { return bar_base + 8u * (3 * STAGES + NBUF + b); };    // ... drained by the epilogue
     auto bar_res = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 * NBUF + b); };   // residual chunk landed in epilogue slot b (group * EPI_SLOTS + slot)
     auto bar_ring = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 * NBUF + 2 * Cfg::EPI_SLOTS + b); };   // ... in ring slot b (group * RING + r)
+    const uint32_t bar_bres = bar_base + 8u * (Cfg::NUM_BARS - 1);      // WS: the resident weights landed (once per CTA)
+    const uint32_t bres_base = smem_base + Cfg::BRES_OFF;
     const uint32_t tmem_slot = bar_base + 8u * Cfg::NUM_BARS;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(epi_gen + Cfg::EPI_BYTES + Cfg::RING_BYTES + 8 * Cfg::NUM_BARS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     // pipeline steps per tile: one k-block (32 channels of one filter tap) -- or, HALO, one (filter row, 32-channel block) = 3 taps
-    const int num_kb = HALO ? p.kh * p.cin_blocks : p.ntaps * p.cin_blocks;
+    const int num_kb = HALO == 1 ? p.kh * p.cin_blocks : (HALO == 2 ? 2 : p.ntaps * p.cin_blocks);
     const int num_items = p.m_pairs * p.n_tiles;
     const int pair = blockIdx.x >> 1;
     const int num_pairs = gridDim.x >> 1;
@@ -206,6 +219,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
         }
         for (int b = 0; b < 2 * Cfg::EPI_SLOTS; ++b) mbar_init(bar_res(b), 1);
         for (int b = 0; b < 2 * RING; ++b) mbar_init(bar_ring(b), 1);
+        if constexpr (WS) mbar_init(bar_bres, 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -239,6 +253,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
         if (lane == 0) {
             const uint32_t tx_bytes = (uint32_t)p.a_tile_bytes + (p.passes == 3 ? 2u : 1u) * Cfg::B_BYTES;
             uint32_t it = 0;
+            if constexpr (WS) {
+                // this CTA's 32 rows of every k-block of the weight matrix (hi, lo), once
+                const int nkb_all = HALO == 1 ? p.kh * p.kw * p.cin_blocks : 7;
+                mbar_arrive_expect_tx(bar_bres, (uint32_t)nkb_all * 2u * Cfg::B_BYTES);
+                for (int kbg = 0; kbg < nkb_all; ++kbg) {
+                    tma_load_2d(bres_base + kbg * 2 * Cfg::B_BYTES, &p.tm_bhi, bar_bres, kbg * 32, (int)cta_rank * (BLOCK_N / 2));
+                    tma_load_2d(bres_base + kbg * 2 * Cfg::B_BYTES + Cfg::B_BYTES, &p.tm_blo, bar_bres, kbg * 32, (int)cta_rank * (BLOCK_N / 2));
+                }
+            }
             for (int item = pair; item < num_items; item += num_pairs) {
                 int w0, h0, n0img, n0;
                 tile_of(item, w0, h0, n0img, n0);
@@ -246,17 +269,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(bar_empty(s), ph ^ 1u);
-                    if constexpr (HALO) {
+                    if constexpr (HALO == 2) {
+                        // step = parity q of the filter rows: the two plane boxes (stride 2 in h from row 2 h0 + q) + the weights of its 4 - q taps
+                        const int q = kb, ntq = 4 - q;
+                        const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
+                        mbar_arrive_expect_tx(bar_full(s), 2u * (uint32_t)p.a_halo_bytes + (WS ? 0u : (uint32_t)ntq * 2u * Cfg::B_BYTES));
+                        tma_load_4d(st, &p.tm_a, bar_full(s), 0, w0, 2 * h0 + q, n0img);
+                        tma_load_4d(st + Cfg::HALO_PLANE_BYTES, &p.tm_a2, bar_full(s), 0, w0, 2 * h0 + q, n0img);
+                        const int nrow = n0 + (int)cta_rank * (BLOCK_N / 2);
+                        for (int j = 0; j < ntq && !WS; ++j) {
+                            const int kbg = 2 * j + q;         // filter row = k-block of the weight matrix
+                            const uint32_t bh = st + Cfg::A_STAGE_BYTES + j * 2 * Cfg::B_BYTES, bl = bh + Cfg::B_BYTES;
+                            if constexpr (kTwoSM) {
+                                tma_load_2d(bh, &p.tm_bhi, bar_full(s), kbg * 32, nrow);
+                                tma_load_2d(bl, &p.tm_blo, bar_full(s), kbg * 32, nrow);
+                            } else {
+                                const uint32_t half = cta_rank * (Cfg::B_BYTES / 2);
+                                tma_load_2d_mcast(bh + half, &p.tm_bhi, bar_full(s), kbg * 32, nrow, (uint16_t)3);
+                                tma_load_2d_mcast(bl + half, &p.tm_blo, bar_full(s), kbg * 32, nrow, (uint16_t)3);
+                            }
+                        }
+                        continue;
+                    }
+                    if constexpr (HALO == 1) {
                         // step = (filter row fy, channel block cb): the two halo planes + the hi / lo weights of the row's three taps
                         const int fy = kb / p.cin_blocks;
                         const int cb = kb - fy * p.cin_blocks;
                         const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
-                        mbar_arrive_expect_tx(bar_full(s), 2u * (uint32_t)p.a_halo_bytes + 6u * Cfg::B_BYTES);
+                        mbar_arrive_expect_tx(bar_full(s), 2u * (uint32_t)p.a_halo_bytes + (WS ? 0u : 6u * Cfg::B_BYTES));
                         tma_load_4d(st, &p.tm_a, bar_full(s), cb * 32, w0 - 1, h0 + fy - 1, n0img);
                         tma_load_4d(st + Cfg::HALO_PLANE_BYTES, &p.tm_a2, bar_full(s), cb * 32, w0 - 1, h0 + fy - 1, n0img);
                         const int nrow = n0 + (int)cta_rank * (BLOCK_N / 2);
 #pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
+                        for (int dx = 0; dx < 3 && !WS; ++dx) {
                             const int kbg = (fy * 3 + dx) * p.cin_blocks + cb;
                             const uint32_t bh = st + Cfg::A_STAGE_BYTES + dx * 2 * Cfg::B_BYTES, bl = bh + Cfg::B_BYTES;
                             if constexpr (kTwoSM) {
@@ -330,7 +375,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
-                    if constexpr (HALO) {
+                    if constexpr (HALO == 2) {
+                        // tap j of this parity reads the box from row slab j on (8 rows = one swizzle atom per slab: plain descriptors)
+                        constexpr int NM = NMAIN == 0 ? 1 : NMAIN;
+                        const uint32_t acc_x = acc0 + (uint32_t)(NMAIN * BLOCK_N);
+                        const int ntq = 4 - kb;
+                        for (int j = 0; j < ntq; ++j) {
+                            const uint64_t da = umma_desc_k_sw64(st + j * 512);
+                            const uint64_t dal = umma_desc_k_sw64(st + Cfg::HALO_PLANE_BYTES + j * 512);
+                            const uint32_t bsm = WS ? bres_base + (2 * j + kb) * 2 * Cfg::B_BYTES : st + Cfg::A_STAGE_BYTES + j * 2 * Cfg::B_BYTES;
+                            const uint64_t dbh = umma_desc_k_sw64(bsm);
+                            const uint64_t dbl = umma_desc_k_sw64(bsm + Cfg::B_BYTES);
+                            const int idx = kb * 4 + j;
+                            const uint32_t acc_main = acc0 + (uint32_t)((idx % NM) * BLOCK_N);
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; ++k) {
+                                const uint64_t koff = (uint64_t)(k * 32 >> 4);
+                                const uint32_t main_flag = NMAIN == 0 ? 1u : ((idx >= NMAIN || k != 0) ? 1u : 0u);
+                                mma(acc_x, dal + koff, dbh + koff, (idx | k) != 0);
+                                mma(acc_x, da + koff, dbl + koff, 1u);
+                                mma(acc_main, da + koff, dbh + koff, main_flag);
+                            }
+                        }
+                    } else if constexpr (HALO == 1) {
                         // tap dx of this filter row reads the halo box from pixel column dx on: start + dx rows, 10 rows between 8-pixel groups
                         constexpr int NM = NMAIN == 0 ? 1 : NMAIN;
                         const uint32_t acc_x = acc0 + (uint32_t)(NMAIN * BLOCK_N);
@@ -338,8 +405,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                         for (int dx = 0; dx < 3; ++dx) {
                             const uint64_t da = umma_desc_k_sw64_sbo(st + dx * 64, 640);
                             const uint64_t dal = umma_desc_k_sw64_sbo(st + Cfg::HALO_PLANE_BYTES + dx * 64, 640);
-                            const uint64_t dbh = umma_desc_k_sw64(st + Cfg::A_STAGE_BYTES + dx * 2 * Cfg::B_BYTES);
-                            const uint64_t dbl = umma_desc_k_sw64(st + Cfg::A_STAGE_BYTES + dx * 2 * Cfg::B_BYTES + Cfg::B_BYTES);
+                            // WS: k-block (fy, dx, cb) of the resident weights; this step is (fy, cb) = (kb / cin_blocks, kb % cin_blocks)
+                            const uint32_t bsm = WS ? bres_base + (((kb / p.cin_blocks) * 3 + dx) * p.cin_blocks + kb % p.cin_blocks) * 2 * Cfg::B_BYTES
+                                                    : st + Cfg::A_STAGE_BYTES + dx * 2 * Cfg::B_BYTES;
+                            const uint64_t dbh = umma_desc_k_sw64(bsm);
+                            const uint64_t dbl = umma_desc_k_sw64(bsm + Cfg::B_BYTES);
                             const int idx = kb * 3 + dx;       // the main term rotates over the accumulators by tap
                             const uint32_t acc_main = acc0 + (uint32_t)((idx % NM) * BLOCK_N);
 #pragma unroll
@@ -399,6 +469,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
         // ================================================================ A_lo converters (128 threads)
         const int ct = threadIdx.x - 64;    // 0..CONV_THREADS-1
         uint32_t it = 0;
+        // WS: a stage is passed on only after this CTA's resident weights have landed (2-SM: the leader's issuer waits for both CTAs' converters)
+        if constexpr (WS) mbar_wait(bar_bres, 0u);
         for (int item = pair; item < num_items; item += num_pairs) {
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
                 const int s = it % STAGES;
@@ -576,9 +648,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                 uint8_t* slot_gen = epi_gen + sidx * Cfg::A_BYTES;
                 // upsample operand of this chunk: requested from global BEFORE the TMEM reads (latency overlap)
                 float4 rr[8];
-                {
+                if (p.res_mode == RES_UPSAMPLE2X) {
                     const float* rp = nullptr;
-                    if (p.res_mode == RES_UPSAMPLE2X && row_valid) {
+                    if (row_valid) {
                         const int uy = min((h0 + ph_) >> 1, p.up_h - 1), ux = min((w0 + pw_) >> 1, p.up_w - 1);
                         rp = p.up_src + (((size_t)(n0img + pn_) * p.up_h + uy) * p.up_w + ux) * (size_t)p.cout + ch0;
                     }
@@ -621,54 +693,79 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                     }
                 }
                 float* stg = reinterpret_cast<float*>(slot_gen + row * 128);
+                // The chunk's arithmetic runs as PASSES over this row's 32 values with the (warp-uniform) mode branches BETWEEN the passes: inside
+                // a pass the 8 pieces are straight-line code, so the 16 scale / shift loads and the shared-memory reads of a pass are all in
+                // flight together.  (Per-piece branches serialised them: ncu source view of the stem, 820 executed instructions and ~7600
+                // cycles per chunk, a third of the stall samples on the reconvergence points behind the per-piece loads.)
+                float o[32];
+                if (ch0 + 32 <= p.cout) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {       // 8 x 16-byte pieces of this row's 128-byte line
-                    const int chj = ch0 + j * 4;
-                    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (chj < p.cout) {                // cout is a multiple of 4 (host pads)
-                        sc = __ldg(reinterpret_cast<const float4*>(p.scale + chj));
-                        sh = __ldg(reinterpret_cast<const float4*>(p.shift + chj));
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + ch0) + j);
+                        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + ch0) + j);
+                        o[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
+                        o[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
+                        o[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
+                        o[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
                     }
-                    float4 o;
-                    o.x = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
-                    o.y = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
-                    o.z = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
-                    o.w = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
-                    const int pj = j ^ (row & 7);      // SWIZZLE_128B: 16-byte piece index XOR (row mod 8)
-                    float4* sl = reinterpret_cast<float4*>(stg) + pj;
-                    if (p.res_mode == RES_TILE) {
-                        const float4 r = (RING > 0) ? rsrc[pj] : *sl;
-                        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                    } else {
-                        o.x += rr[j].x; o.y += rr[j].y; o.z += rr[j].z; o.w += rr[j].w;       // zeros when there is no operand
-                    }
-                    if (p.relu) {
-                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                    }
-                    if (chj < p.sigmoid_ch) {
-                        // torch.sigmoid on CPU evaluates 1/(1+exp(-x)); expf/div are IEEE-rounded here
-                        if (chj + 0 < p.sigmoid_ch) o.x = 1.f / (1.f + expf(-o.x));
-                        if (chj + 1 < p.sigmoid_ch) o.y = 1.f / (1.f + expf(-o.y));
-                        if (chj + 2 < p.sigmoid_ch) o.z = 1.f / (1.f + expf(-o.z));
-                        if (chj + 3 < p.sigmoid_ch) o.w = 1.f / (1.f + expf(-o.w));
-                    }
-                    if (KIND == KIND_F16X3 && p.out_planes) {
-                        // two 64-byte-row fp16 tiles in the 16 KB slot (hi | lo), SWIZZLE_64B: this row's 8-byte piece j of the 64-byte line
-                        if (!(fabsf(o.x) < 65504.f) || !(fabsf(o.y) < 65504.f) || !(fabsf(o.z) < 65504.f) || !(fabsf(o.w) < 65504.f)) {
-                            if (p.range_flag && chj < p.cout && row * 128 < p.a_tile_bytes) *p.range_flag = 1;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {       // the last, partial chunk of a Cout that is not a multiple of 32 (cout % 4 == 0: host pads)
+                        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ch0 + j * 4 < p.cout) {
+                            sc = __ldg(reinterpret_cast<const float4*>(p.scale + ch0) + j);
+                            sh = __ldg(reinterpret_cast<const float4*>(p.shift + ch0) + j);
                         }
-                        const __half2 h01 = __floats2half2_rn(o.x, o.y), h23 = __floats2half2_rn(o.z, o.w);
+                        o[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
+                        o[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
+                        o[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
+                        o[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
+                    }
+                }
+                if (p.res_mode == RES_TILE) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int pj = j ^ (row & 7);      // SWIZZLE_128B: 16-byte piece index XOR (row mod 8)
+                        const float4 r = (RING > 0) ? rsrc[pj] : reinterpret_cast<const float4*>(stg)[pj];
+                        o[4 * j + 0] += r.x; o[4 * j + 1] += r.y; o[4 * j + 2] += r.z; o[4 * j + 3] += r.w;
+                    }
+                } else if (p.res_mode == RES_UPSAMPLE2X) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { o[4 * j + 0] += rr[j].x; o[4 * j + 1] += rr[j].y; o[4 * j + 2] += rr[j].z; o[4 * j + 3] += rr[j].w; }
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
+                }
+                if (ch0 < p.sigmoid_ch) {
+                    // torch.sigmoid on CPU evaluates 1/(1+exp(-x)); expf/div are IEEE-rounded here
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (ch0 + j < p.sigmoid_ch) o[j] = 1.f / (1.f + expf(-o[j]));
+                }
+                if (KIND == KIND_F16X3 && p.out_planes) {
+                    // two 64-byte-row fp16 tiles in the 16 KB slot (hi | lo), SWIZZLE_64B: this row's 8-byte piece j of the 64-byte line
+                    bool bad = false;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float ox = o[4 * j + 0], oy = o[4 * j + 1], oz = o[4 * j + 2], ow = o[4 * j + 3];
+                        bad = bad || !(fabsf(ox) < 65504.f) || !(fabsf(oy) < 65504.f) || !(fabsf(oz) < 65504.f) || !(fabsf(ow) < 65504.f);
+                        const __half2 h01 = __floats2half2_rn(ox, oy), h23 = __floats2half2_rn(oz, ow);
                         const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                        const __half2 l01 = __floats2half2_rn(o.x - f01.x, o.y - f01.y), l23 = __floats2half2_rn(o.z - f23.x, o.w - f23.y);
+                        const __half2 l01 = __floats2half2_rn(ox - f01.x, oy - f01.y), l23 = __floats2half2_rn(oz - f23.x, ow - f23.y);
                         const int off = row * 64 + ((((j >> 1) ^ ((row >> 1) & 3)) << 4) | ((j & 1) << 3));
                         uint2 hv, lv;
                         hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
                         lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
                         *reinterpret_cast<uint2*>(slot_gen + off) = hv;
                         *reinterpret_cast<uint2*>(slot_gen + Cfg::A_BYTES / 2 + off) = lv;
-                    } else {
-                        *sl = o;
                     }
+                    // (out_planes layers have Cout % 32 == 0: every channel of the chunk is live)
+                    if (bad && p.range_flag && row * 128 < p.a_tile_bytes) *p.range_flag = 1;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        reinterpret_cast<float4*>(stg)[j ^ (row & 7)] = make_float4(o[4 * j + 0], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(1 + g, 128);

@@ -60,6 +60,43 @@ static __global__ void stem_pack_nhwc4_kernel(const float* __restrict__ img, int
     }
 }
 
+// fp16 hi/lo split of four fp32 values (h = fp16(v), l = fp16(v - h): the operand format of the kind::f16 three-term product); `bad`
+// is raised when a value does not fit fp16
+__device__ __forceinline__ void split_planes4(float4 v, uint2* hi, uint2* lo, bool* bad) {
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    __half h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        h[j] = __float2half_rn(f[j]);
+        l[j] = __float2half_rn(f[j] - __half2float(h[j]));
+        *bad = *bad || !(fabsf(f[j]) < 65504.f);
+    }
+    *hi = *reinterpret_cast<const uint2*>(h);
+    *lo = *reinterpret_cast<const uint2*>(l);
+}
+
+// stem_pack_nhwc4_kernel emitting the two fp16 planes [B, Hp, Wp, 4] the kind::f16 stem loads straight into its operand tiles
+static __global__ void stem_pack_nhwc4_planes_kernel(const float* __restrict__ img, int B, int H, int W, int Hp, int Wp, uint2* __restrict__ xh,
+                                                     uint2* __restrict__ xl, int* __restrict__ range_flag) {
+    const long long total = (long long)B * Hp * Wp;
+    bool bad = false;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int xp = (int)(i % Wp);
+        const int yp = (int)((i / Wp) % Hp);
+        const int b = (int)(i / ((long long)Wp * Hp));
+        const int x = xp - 3, y = yp - 3;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x >= 0 && x < W && y >= 0 && y < H) {
+            const size_t o = ((size_t)b * 3 * H + y) * W + x;
+            v.x = __ldg(img + o); v.y = __ldg(img + o + (size_t)H * W); v.z = __ldg(img + o + 2 * (size_t)H * W);
+        }
+        uint2 h, l;
+        split_planes4(v, &h, &l, &bad);
+        xh[i] = h; xl[i] = l;
+    }
+    if (bad && range_flag) *range_flag = 1;
+}
+
 // NHWC 3x3 stride-2 pad-1 max pool (torchvision maxpool)
 static __global__ void maxpool3x3s2_nhwc_kernel(const float* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo, float* __restrict__ y) {
     const int C4 = C >> 2;

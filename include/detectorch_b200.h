@@ -189,7 +189,8 @@ typedef struct dt_engine_config {
     int conv_kind;               /* 0 = three-term product on the kind::f16 pipe (fp16 hi/lo halves, default: twice the tf32 issue rate; an
                                     activation >= 65504 raises the int32 buffer "range_flag"), 1 = 3xTF32 (no range limit) */
     int plane_handover;          /* kind::f16 only: 1 = conv1 of every bottleneck writes its output as two fp16 planes (hi, lo) that conv2 (3x3)
-                                    loads straight into its operand tiles (no per-tap re-conversion); 0 = fp32 hand-over */
+                                    loads straight into its operand tiles (no per-tap re-conversion); 2 = conv2 -> conv3 as well; 3 = also the
+                                    packed image -> stem and the pooled map -> first bottleneck (FPN engine); 0 = fp32 hand-over */
 } dt_engine_config;
 
 typedef void* dt_engine_t;
