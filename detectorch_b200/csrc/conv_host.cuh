@@ -198,6 +198,13 @@ inline int conv_ws_mode() {
     return v;
 }
 
+// DT_CONV_NARROW1=0: 64-wide short-K layers and the stem keep 3 rotating accumulators (A/B, tests)
+inline bool conv_narrow_one_acc() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DT_CONV_NARROW1"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
 // Persistent launch geometry: work items = (pairs of M-tiles) x (N-tiles); one 2-CTA cluster per SM pair (74 on B200),
 // each looping over items pair, pair + num_pairs, ...  An odd M-tile count gets one all-out-of-range surplus tile (TMA
 // zero-fills its loads and clips its stores) so that both CTAs of a pair always run the same multicast protocol.
@@ -307,7 +314,10 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
     // merged accumulator leaves room for two tiles (measured: -0.7 ms per step when applied to every layer up to K = 2304); the price is
     // a 3x longer truncating-accumulate chain (main and both cross terms in one accumulator), which the trunk / FPN / RPN / box-head
     // activations can afford (they sit at 1e-5 of their 1e-4 bar) and the mask-head layers cannot (no_merge).
-    L->nmain = (bn == 64) ? 3 : ((bn == 128 && s.precise) ? 3 : ((bn == 256 && !s.no_merge && conv_merge_acc(p.ntaps * p.cin_blocks)) ? 0 : 1));
+    // 64-wide tiles rotate the main term over 3 accumulators (short truncating-accumulate chains at no TMEM cost) -- except at K <= 256, where
+    // one accumulator already is a chain of at most 16 steps and the two extra TMEM reads + RN adds per chunk only lengthen the epilogue
+    const bool narrow1 = bn == 64 && s.kind == KIND_F16X3 && !L->halo && p.ntaps * p.cin_blocks <= 8 && conv_narrow_one_acc();
+    L->nmain = (bn == 64) ? (narrow1 ? 1 : 3) : ((bn == 128 && s.precise) ? 3 : ((bn == 256 && !s.no_merge && conv_merge_acc(p.ntaps * p.cin_blocks)) ? 0 : 1));
     finish_grid(L, ceil_div(s.Cout, bn));
     {
         static int use_ring = -1;
@@ -334,6 +344,7 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
     // than the streaming form (167 -> 175 us; the stem gains 17 %), so it is opt-in here (DT_CONV_WS=2)
     L->ws = L->halo == 1 && bn == 64 && conv_ws_mode() == 2 && s.Cout <= 64 && s.kh * s.kw * p.cin_blocks <= 18;
     if (L->ws) L->two_sm = true;
+    if (L->nmain == 1 && bn == 64 && L->slots != 2) L->nmain = 3;       // the one-accumulator 64-wide kernel exists with two staging slots only
     if (L->halo && (L->nmain != (bn == 64 ? 3 : 1) || L->two_sm != (bn == 128 || L->ws) || L->ring)) {
         fprintf(stderr, "[detectorch_b200] conv_build: halo layer ended up in an instantiation the halo kernel does not cover\n");
         return false;
@@ -397,6 +408,7 @@ inline bool conv_build_stem(const float* x4, int B, int Hp, int Wp, int H1, int 
     finish_grid(L, 1);
     L->ws = L->halo == 2 && conv_ws_mode() >= 1;
     if (L->ws) L->two_sm = true;
+    if (L->ws && conv_narrow_one_acc()) L->nmain = 1;       // K = 7 k-blocks: one main accumulator (see conv_build)
     return true;
 }
 
@@ -444,7 +456,9 @@ inline cudaError_t conv_launch_sm(const ConvLayer& L, cudaStream_t stream) {
             if constexpr (TWO) {
                 if (L.block_n == 128 && L.halo == 1) return conv_launch_cfg<128, 1, true, KIND_F16X3, 0, 2, 1>(L, stream);
                 if (L.block_n == 64 && L.halo == 1 && L.ws) return conv_launch_cfg<64, 3, true, KIND_F16X3, 0, 2, 1, true>(L, stream);
-                if (L.block_n == 64 && L.halo == 2 && L.ws) return conv_launch_cfg<64, 3, true, KIND_F16X3, 0, 2, 2, true>(L, stream);
+                if (L.block_n == 64 && L.halo == 2 && L.ws)
+                    return L.nmain == 1 ? conv_launch_cfg<64, 1, true, KIND_F16X3, 0, 2, 2, true>(L, stream)
+                                        : conv_launch_cfg<64, 3, true, KIND_F16X3, 0, 2, 2, true>(L, stream);
             } else {
                 if (L.block_n == 64 && L.halo == 1) return conv_launch_cfg<64, 3, false, KIND_F16X3, 0, 2, 1>(L, stream);
                 if (L.block_n == 64 && L.halo == 2) return conv_launch_cfg<64, 3, false, KIND_F16X3, 0, 2, 2>(L, stream);
@@ -453,7 +467,9 @@ inline cudaError_t conv_launch_sm(const ConvLayer& L, cudaStream_t stream) {
         }
     }
     switch (L.block_n) {
-        case 64: return s2 ? conv_launch_cfg<64, 3, TWO, KIND, 0, S2>(L, stream) : conv_launch_cfg<64, 3, TWO, KIND, 0, 1>(L, stream);
+        case 64:
+            if constexpr (kCan2) { if (L.nmain == 1 && s2) return conv_launch_cfg<64, 1, TWO, KIND, 0, 2>(L, stream); }
+            return s2 ? conv_launch_cfg<64, 3, TWO, KIND, 0, S2>(L, stream) : conv_launch_cfg<64, 3, TWO, KIND, 0, 1>(L, stream);
         case 128:
             if (L.nmain == 3) return s2 ? conv_launch_cfg<128, 3, TWO, KIND, 0, S2>(L, stream) : conv_launch_cfg<128, 3, TWO, KIND, 0, 1>(L, stream);
             return s2 ? conv_launch_cfg<128, 1, TWO, KIND, 0, S2>(L, stream) : conv_launch_cfg<128, 1, TWO, KIND, 0, 1>(L, stream);
