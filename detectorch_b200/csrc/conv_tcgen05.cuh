@@ -581,37 +581,53 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
             int nl = (p.cout - (item_ % p.n_tiles) * BLOCK_N + 31) / 32;       // chunks past the true Cout are neither computed nor stored
             return nl < 0 ? 0 : (nl > NCHUNK ? NCHUNK : nl);
         };
-        // the group's next chunk after (item_, c_): same tile, or the first live chunk of a later tile
-        auto next_chunk = [&](int& item_, int& c_) {
-            c_ += 2;
-            while (item_ < num_items && c_ >= nlive_of(item_)) { item_ += num_pairs; c_ = g; }
-            return item_ < num_items;
+        // A cursor over this group's live chunks in processing order.  The tile fields are recomputed only when the item changes: thread 0
+        // advances two of these per chunk between the group's barriers (the other 127 threads wait for it), and the divisions of tile_of /
+        // nlive_of per chunk were a quarter of the chunk time of the short-K layers (ncu source view: 31 % of the epilogue warps' samples
+        // on the barrier that follows thread 0's bookkeeping).
+        struct Cursor { int item, c, nlive, w0, h0, n0img, n0; };
+        auto cur_init = [&](Cursor& k) {
+            k.item = pair; k.c = g - 2;
+            k.nlive = nlive_of(k.item);
+            tile_of(k.item, k.w0, k.h0, k.n0img, k.n0);
         };
-        auto issue_residual = [&](int item_, int c_, uint32_t gcn) {     // et == 0 only: residual tile chunk -> slot of chunk number gcn
-            int w0_, h0_, n0img_, n0_;
-            tile_of(item_, w0_, h0_, n0img_, n0_);
+        auto cur_next = [&](Cursor& k) {        // -> the group's next live chunk (same tile, or the first live chunk of a later tile)
+            k.c += 2;
+            if (k.c < k.nlive) return true;
+            do {
+                k.item += num_pairs; k.c = g;
+                if (k.item >= num_items) return false;
+                k.nlive = nlive_of(k.item);
+            } while (k.c >= k.nlive);
+            tile_of(k.item, k.w0, k.h0, k.n0img, k.n0);
+            return true;
+        };
+        auto issue_residual = [&](const Cursor& k, uint32_t gcn) {     // et == 0 only: residual tile chunk -> slot of chunk number gcn
             const uint32_t sl = (uint32_t)(g * NS) + (gcn % NS);
             mbar_arrive_expect_tx(bar_res(sl), (uint32_t)p.a_tile_bytes);
-            tma_load_4d(epi_base + sl * Cfg::A_BYTES, &p.tm_r, bar_res(sl), n0_ + c_ * 32, w0_, h0_, n0img_);
+            tma_load_4d(epi_base + sl * Cfg::A_BYTES, &p.tm_r, bar_res(sl), k.n0 + k.c * 32, k.w0, k.h0, k.n0img);
         };
         // RING > 0: a separate prefetch stream runs RING chunks ahead of the consumer
-        int pf_item = pair, pf_c = g - 2;
+        Cursor pf, nx;                          // prefetch position (ring); the chunk after the one being processed
+        bool pf_live = true;
+        if (et == 0) { cur_init(pf); cur_init(nx); }
         uint32_t pf_n = 0;                      // chunks whose residual load has been issued
         auto issue_ring = [&]() {               // et == 0 only
-            if (!next_chunk(pf_item, pf_c)) return;
-            int w0_, h0_, n0img_, n0_;
-            tile_of(pf_item, w0_, h0_, n0img_, n0_);
+            if (!pf_live) return;
+            pf_live = cur_next(pf);
+            if (!pf_live) return;
             const uint32_t sl = (uint32_t)(g * RING) + (pf_n % (RING > 0 ? RING : 1));
             mbar_arrive_expect_tx(bar_ring(sl), (uint32_t)p.a_tile_bytes);
-            tma_load_4d(ring_base + sl * Cfg::A_BYTES, &p.tm_r, bar_ring(sl), n0_ + pf_c * 32, w0_, h0_, n0img_);
+            tma_load_4d(ring_base + sl * Cfg::A_BYTES, &p.tm_r, bar_ring(sl), pf.n0 + pf.c * 32, pf.w0, pf.h0, pf.n0img);
             ++pf_n;
         };
+        bool nx_live = true;
+        if (et == 0) nx_live = cur_next(nx);    // nx = the group's first chunk
         if (et == 0 && p.res_mode == RES_TILE) {
             if constexpr (RING > 0) {
                 for (int r = 0; r < RING; ++r) issue_ring();
             } else {                                   // residual of the group's very first chunk
-                int it0 = pair, c0 = g - 2;
-                if (next_chunk(it0, c0)) issue_residual(it0, c0, 0u);
+                if (nx_live) issue_residual(nx, 0u);
             }
         }
         int t = 0;
@@ -660,6 +676,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                 }
                 // the accumulator read does not depend on the staging slot: request it BEFORE the group barrier, so that the TMEM latency
                 // overlaps the wait for thread 0 (slot hand-over / residual issue) instead of following it
+                const bool full_chunk = ch0 + 32 <= p.cout;
                 uint32_t v[32];
                 const uint32_t tbase = tbase0 + (uint32_t)(c * 32);
                 tmem_ld_32x32(tbase, v);
@@ -697,8 +714,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                 // a pass the 8 pieces are straight-line code, so the 16 scale / shift loads and the shared-memory reads of a pass are all in
                 // flight together.  (Per-piece branches serialised them: ncu source view of the stem, 820 executed instructions and ~7600
                 // cycles per chunk, a third of the stall samples on the reconvergence points behind the per-piece loads.)
+                // (Measured and rejected: fetching the scale / shift vectors ahead of the group barrier -- 64 more live registers spill.)
                 float o[32];
-                if (ch0 + 32 <= p.cout) {
+                if (full_chunk) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + ch0) + j);
@@ -779,14 +797,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                     tma_store_commit();
                     // free the slot the NEXT chunk will use (its last store must have finished reading shared memory) and start that
                     // chunk's residual load, so that both overlap the next chunk's TMEM reads
-                    int itn = item, cn = c;
+                    nx_live = cur_next(nx);        // nx was this chunk: now the next one
                     if constexpr (RING > 0) {
                         // every thread of the group is past its reads of this chunk's ring slot (named barrier above): refill it
                         if (p.res_mode == RES_TILE) issue_ring();
-                        if (next_chunk(itn, cn)) tma_store_wait_read<NS - 1>();
-                    } else if (next_chunk(itn, cn)) {
+                        if (nx_live) tma_store_wait_read<NS - 1>();
+                    } else if (nx_live) {
                         tma_store_wait_read<NS - 1>();
-                        if (p.res_mode == RES_TILE) issue_residual(itn, cn, gc + 1);
+                        if (p.res_mode == RES_TILE) issue_residual(nx, gc + 1);
                     }
                 }
             }
