@@ -159,7 +159,8 @@ struct ConvCfg {
     static constexpr int CONV_WARPS = (KIND == KIND_F16X3 && BLOCK_N <= 128) ? DT_CONV_WARPS_NARROW : 4;
     static constexpr int CONV_THREADS = CONV_WARPS * 32;
     static constexpr int EPI_WARP0 = 2 + CONV_WARPS;                 // first epilogue warp
-    static constexpr int THREADS = 64 + CONV_THREADS + 256;
+    static constexpr int STORE_WARP0 = EPI_WARP0 + 8;                // two store warps (one per epilogue group) follow the 8 epilogue warps
+    static constexpr int THREADS = 64 + CONV_THREADS + 256 + 64;
     static_assert(TILE_COLS <= 512, "accumulators of one tile must fit TMEM");
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory limit");
     static_assert(8 * (NUM_BARS + 1) <= 256, "barrier area");
@@ -570,9 +571,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
         // ================================================================ epilogue: two independent groups of 4 warps (warps 6-9, 10-13)
         // Group g drains the live 32-channel chunks c with c % 2 == g through its own 16 KB staging slot, so two chunks are in
         // flight per tile and every SM sub-partition has two epilogue warps to hide TMEM / shared / global latencies.
+        // Each group has a STORE WARP (warps STORE_WARP0 + g): it issues the chunk's TMA store, does the tile bookkeeping, refills the residual
+        // ring and waits for the next staging slot to drain, while the 128 workers are already reading and summing the next chunk's
+        // accumulators.  Two named barriers per group pair them: B2 (id 4 + g: workers arrive after writing + fencing the staging slot, the
+        // store warp waits) and B1 (id 1 + g: the store warp arrives once the next chunk's slot is free, the workers wait right before
+        // they write it).  With the store inside the worker group (thread 0) the other 127 threads idled through its bookkeeping: ncu
+        // showed 31 % of the epilogue warps' samples on that barrier in the short-K layers.
         constexpr int NCHUNK = BLOCK_N / 32;
-        const int g = (warp - Cfg::EPI_WARP0) >> 2;
-        const int et = threadIdx.x - (64 + Cfg::CONV_THREADS) - 128 * g;   // 0..127 within the group
+        const bool is_store = warp >= Cfg::STORE_WARP0;
+        const int g = is_store ? warp - Cfg::STORE_WARP0 : (warp - Cfg::EPI_WARP0) >> 2;
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;          // accumulator row == pixel slot in the box
         constexpr int NS = Cfg::EPI_SLOTS;
@@ -607,29 +614,63 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
             mbar_arrive_expect_tx(bar_res(sl), (uint32_t)p.a_tile_bytes);
             tma_load_4d(epi_base + sl * Cfg::A_BYTES, &p.tm_r, bar_res(sl), k.n0 + k.c * 32, k.w0, k.h0, k.n0img);
         };
-        // RING > 0: a separate prefetch stream runs RING chunks ahead of the consumer
-        Cursor pf, nx;                          // prefetch position (ring); the chunk after the one being processed
-        bool pf_live = true;
-        if (et == 0) { cur_init(pf); cur_init(nx); }
-        uint32_t pf_n = 0;                      // chunks whose residual load has been issued
-        auto issue_ring = [&]() {               // et == 0 only
-            if (!pf_live) return;
-            pf_live = cur_next(pf);
-            if (!pf_live) return;
-            const uint32_t sl = (uint32_t)(g * RING) + (pf_n % (RING > 0 ? RING : 1));
-            mbar_arrive_expect_tx(bar_ring(sl), (uint32_t)p.a_tile_bytes);
-            tma_load_4d(ring_base + sl * Cfg::A_BYTES, &p.tm_r, bar_ring(sl), pf.n0 + pf.c * 32, pf.w0, pf.h0, pf.n0img);
-            ++pf_n;
-        };
-        bool nx_live = true;
-        if (et == 0) nx_live = cur_next(nx);    // nx = the group's first chunk
-        if (et == 0 && p.res_mode == RES_TILE) {
-            if constexpr (RING > 0) {
-                for (int r = 0; r < RING; ++r) issue_ring();
-            } else {                                   // residual of the group's very first chunk
-                if (nx_live) issue_residual(nx, 0u);
+        if (is_store) {
+            // ------------------------------------------------------------ store warp of group g (lane 0 issues; the warp stays convergent for the barriers)
+            Cursor cur, pf;                         // the chunk being stored; the ring prefetch position (RING chunks ahead)
+            cur_init(cur); cur_init(pf);
+            bool live = cur_next(cur), pf_live = true;
+            uint32_t pf_n = 0;                      // chunks whose residual load has been issued
+            auto issue_ring = [&]() {               // lane 0 only
+                if (!pf_live) return;
+                pf_live = cur_next(pf);
+                if (!pf_live) return;
+                const uint32_t sl = (uint32_t)(g * RING) + (pf_n % (RING > 0 ? RING : 1));
+                mbar_arrive_expect_tx(bar_ring(sl), (uint32_t)p.a_tile_bytes);
+                tma_load_4d(ring_base + sl * Cfg::A_BYTES, &p.tm_r, bar_ring(sl), pf.n0 + pf.c * 32, pf.w0, pf.h0, pf.n0img);
+                ++pf_n;
+            };
+            if (lane == 0 && p.res_mode == RES_TILE) {
+                if constexpr (RING > 0) {
+                    for (int r = 0; r < RING; ++r) issue_ring();
+                } else if (live) {                     // residual of the group's very first chunk
+                    issue_residual(cur, 0u);
+                }
             }
-        }
+            __syncwarp();
+            if (live) named_bar_arrive(1 + g, 160);     // the first chunk's slot is free
+            while (live) {
+                named_bar_sync(4 + g, 160);             // the workers have written (and fenced) this chunk's staging slot
+                if (lane == 0) {
+                    const uint32_t sidx = (uint32_t)(g * NS) + (gc % NS);
+                    const uint32_t slot = epi_base + sidx * Cfg::A_BYTES;
+                    const int ch0 = cur.n0 + cur.c * 32;
+                    if (KIND == KIND_F16X3 && p.out_planes) {
+                        tma_store_4d(&p.tm_d, slot, ch0, cur.w0, cur.h0, cur.n0img);
+                        tma_store_4d(&p.tm_d2, slot + Cfg::A_BYTES / 2, ch0, cur.w0, cur.h0, cur.n0img);
+                    } else {
+                        tma_store_4d(&p.tm_d, slot, ch0, cur.w0, cur.h0, cur.n0img);
+                    }
+                    tma_store_commit();
+                }
+                live = cur_next(cur);                   // (every lane keeps the cursor: the loop condition must stay warp-uniform)
+                if (lane == 0) {
+                    // free the slot the NEXT chunk will use (its last store must have finished reading shared memory) and start that
+                    // chunk's residual load
+                    if constexpr (RING > 0) {
+                        // every worker is past its reads of this chunk's ring slot (it arrived on B2): refill it
+                        if (p.res_mode == RES_TILE) issue_ring();
+                        if (live) tma_store_wait_read<NS - 1>();
+                    } else if (live) {
+                        tma_store_wait_read<NS - 1>();
+                        if (p.res_mode == RES_TILE) issue_residual(cur, gc + 1);
+                    }
+                }
+                __syncwarp();
+                if (live) named_bar_arrive(1 + g, 160);
+                ++gc;
+            }
+            if (lane == 0) tma_store_wait0();      // all output bytes written before the CTA may exit
+        } else {
         int t = 0;
         for (int item = pair; item < num_items; item += num_pairs, ++t) {
             int w0, h0, n0img, n0;
@@ -680,9 +721,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                 uint32_t v[32];
                 const uint32_t tbase = tbase0 + (uint32_t)(c * 32);
                 tmem_ld_32x32(tbase, v);
-                // thread 0 of the group has, at the end of the previous chunk, waited until the store that last used this slot finished
-                // reading it and (RES_TILE) started the TMA load of this chunk's residual tile into it
-                named_bar_sync(1 + g, 128);
                 tmem_ld_wait();
 #pragma unroll 1
                 for (int a = 1; a <= NMAIN; ++a) {      // remaining main accumulators, then the cross accumulator
@@ -761,6 +799,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                     for (int j = 0; j < 32; ++j)
                         if (ch0 + j < p.sigmoid_ch) o[j] = 1.f / (1.f + expf(-o[j]));
                 }
+                // B1: the store warp has seen the store that last used this slot finish reading it (non-ring RES_TILE: the residual tile was
+                // loaded into the slot after that, and has been consumed above)
+                named_bar_sync(1 + g, 160);
                 if (KIND == KIND_F16X3 && p.out_planes) {
                     // two 64-byte-row fp16 tiles in the 16 KB slot (hi | lo), SWIZZLE_64B: this row's 8-byte piece j of the 64-byte line
                     bool bad = false;
@@ -786,30 +827,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ConvCfg<BLOCK_N, NM
                         reinterpret_cast<float4*>(stg)[j ^ (row & 7)] = make_float4(o[4 * j + 0], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(1 + g, 128);
-                if (et == 0) {
-                    if (KIND == KIND_F16X3 && p.out_planes) {
-                        tma_store_4d(&p.tm_d, slot, ch0, w0, h0, n0img);
-                        tma_store_4d(&p.tm_d2, slot + Cfg::A_BYTES / 2, ch0, w0, h0, n0img);
-                    } else {
-                        tma_store_4d(&p.tm_d, slot, ch0, w0, h0, n0img);
-                    }
-                    tma_store_commit();
-                    // free the slot the NEXT chunk will use (its last store must have finished reading shared memory) and start that
-                    // chunk's residual load, so that both overlap the next chunk's TMEM reads
-                    nx_live = cur_next(nx);        // nx was this chunk: now the next one
-                    if constexpr (RING > 0) {
-                        // every thread of the group is past its reads of this chunk's ring slot (named barrier above): refill it
-                        if (p.res_mode == RES_TILE) issue_ring();
-                        if (nx_live) tma_store_wait_read<NS - 1>();
-                    } else if (nx_live) {
-                        tma_store_wait_read<NS - 1>();
-                        if (p.res_mode == RES_TILE) issue_residual(nx, gc + 1);
-                    }
-                }
+                named_bar_arrive(4 + g, 160);           // B2: this row of the staging slot is written; the store warp takes it from here
             }
         }
-        if (et == 0) tma_store_wait0();      // all output bytes written before the CTA may exit
+        }
     }
 
     // ---- teardown: neither CTA may exit while the peer can still multicast into it or arrive on its barriers
