@@ -327,16 +327,14 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
         L->ring = (use_ring && L->nmain == 0 && L->two_sm && L->kind == KIND_F16X3 && s.res_mode == RES_TILE && p.ntaps * p.cin_blocks <= 8) ? 1 : 0;
     }
     {
-        // Two staging slots per epilogue group (the TMA store of a chunk drains while the next chunk is computed: -10..16 % on the
-        // epilogue-bound layers) wherever the epilogue is exposed: every tile up to 128 wide, the 256-wide layers with at most 16 k-blocks
-        // per tile (K <= 512), and the 256-wide layers that cannot double-buffer their accumulators (NMAIN = 1: the mask-head K-split
-        // halves, whose epilogue is never overlapped by the next tile's MMAs).  Long-K merged-accumulator layers hide their epilogue behind
-        // the next tile and keep one slot = one more pipeline stage.  With the in-place fp16 split a stage is 32 KB, so even two slots
-        // leave five stages.  DT_CONV_SLOTS=1|2 forces one setting (A/B, tests).
+        // Two staging slots per epilogue group (the TMA store of a chunk drains while the next chunk is computed) for tiles up to 128 wide,
+        // where the extra 32 KB do not cost a pipeline stage.  256-wide tiles take ONE slot = one more pipeline stage: since the store warps
+        // decoupled the stores from the workers, the second slot no longer pays for itself there (same-box sweep, profiles/r02_summary.md:
+        // short-K 256-wide layers -5..20 % with one slot, long-K +15 % with two; with the stores still issued by worker thread 0 the
+        // short-K layers had been 10-16 % faster with two).  DT_CONV_SLOTS=1|2 forces one setting (A/B, tests).
         static int force = -1;
         if (force < 0) { const char* e = getenv("DT_CONV_SLOTS"); force = e ? atoi(e) : 0; }
-        const int kb = p.ntaps * p.cin_blocks;
-        L->slots = (bn <= 128 || (bn == 256 && (L->nmain != 0 || kb <= 16))) ? 2 : 1;
+        L->slots = bn <= 128 ? 2 : 1;
         if (force == 1 || force == 2) L->slots = force;
         if (L->halo) L->slots = 2;
     }
