@@ -518,7 +518,13 @@ cudaError_t fn_stem_pack_planes(Engine* e, cudaStream_t s) {
 }
 cudaError_t fn_maxpool(Engine* e, cudaStream_t s) {
     const long long n = (long long)e->cfg.batch * e->H2 * e->W2 * 16;
-    maxpool3x3s2_nhwc_kernel<<<grid_for(n), 256, 0, s>>>(e->buf("c1"), e->cfg.batch, e->H1, e->W1, 64, e->H2, e->W2, e->buf("pool"));
+    maxpool3x3s2_nhwc_kernel<false><<<grid_for(n), 256, 0, s>>>(e->buf("c1"), e->cfg.batch, e->H1, e->W1, 64, e->H2, e->W2, e->buf("pool"), nullptr);
+    return cudaGetLastError();
+}
+cudaError_t fn_maxpool_planes(Engine* e, cudaStream_t s) {
+    const long long n = (long long)e->cfg.batch * e->H2 * e->W2 * 16;
+    maxpool3x3s2_nhwc_kernel<true><<<grid_for(n), 256, 0, s>>>(e->buf("c1"), e->cfg.batch, e->H1, e->W1, 64, e->H2, e->W2, e->buf("pool"),
+                                                              e->buf<int>("range_flag"));
     return cudaGetLastError();
 }
 
@@ -666,9 +672,10 @@ bool build_program(Engine* e, std::map<std::string, ConvW>* cw) {
             pb.conv(ST_TRUNK, "stem", e->buf("stem_col"), 1, 1, B * e->H1 * e->W1, 160, e->buf("c1"), 64, 0, 1, true);
         }
     }
-    // (measured and rejected: the pooled map as fp16 planes too -- its consumers, conv1 and the downsample conv of the first bottleneck, did
-    // not get faster, the pool kernel got 19 us slower)
-    pb.fn(ST_TRUNK, fn_maxpool);
+    // plane_handover >= 4: the pooled map leaves as fp16 planes too (its two consumers -- conv1 and the downsample conv of the first
+    // bottleneck -- then load their operand tiles directly)
+    const int pool_planes = (c.conv_kind == 0 && c.plane_handover >= 4) ? 1 : 0;
+    pb.fn(ST_TRUNK, pool_planes ? fn_maxpool_planes : fn_maxpool);
     const float* x = e->buf("pool");
     int h = e->H2, w = e->W2, cin = 64;
     for (int li = 1; li <= 4; ++li) {
@@ -681,8 +688,9 @@ bool build_program(Engine* e, std::map<std::string, ConvW>* cw) {
             // conv1 -> conv2 hand-over as fp16 hi/lo planes: the 3x3 conv would otherwise re-convert every input element once per filter tap
             // (the converter warps' fp32->fp16 packs are what bounds the 64/128-wide layers)
             const int pl = c.plane_handover ? 1 : 0;
+            const int xin_planes = (li == 1 && b == 0) ? pool_planes : 0;
             pb.conv(ST_TRUNK, wp + "conv1", x, B, h, w, cin, e->buf(p + ".t1"), planes, 0, stride, true, RES_NONE, nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0,
-                    0, 0, 0, false, 0, pl);
+                    0, 0, 0, false, xin_planes, pl);
             // conv2 -> conv3 the same way (plane_handover >= 2): conv3 is a 1x1 conv, so this saves one conversion per element, the converter
             // warps' shared-memory round trip (16 KB read + 16 KB written per k-block) and their issue slots in the epilogue-bound conv3
             const int pl2 = c.plane_handover >= 2 ? 1 : 0;
@@ -690,7 +698,8 @@ bool build_program(Engine* e, std::map<std::string, ConvW>* cw) {
                     0, 0, 0, 0, 0, 0, 0, 0, 0, false, pl, pl2);
             const float* idt = x;
             if (b == 0) {
-                pb.conv(ST_TRUNK, wp + "downsample.0", x, B, h, w, cin, e->buf(p + ".ds"), planes * 4, 0, stride, false);
+                pb.conv(ST_TRUNK, wp + "downsample.0", x, B, h, w, cin, e->buf(p + ".ds"), planes * 4, 0, stride, false, RES_NONE, nullptr, nullptr, 0, 0, 0,
+                        0, 0, 0, 0, 0, 0, 0, 0, 0, false, xin_planes, 0);
                 idt = e->buf(p + ".ds");
             }
             pb.conv(ST_TRUNK, wp + "conv3", e->buf(p + ".t2"), B, ho, wo, planes, e->buf(p + ".out"), planes * 4, 0, 1, true, RES_TILE, idt, nullptr, 0, 0, 0,
