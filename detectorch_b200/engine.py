@@ -146,7 +146,7 @@ class Engine:
         if conv_kind not in ("f16", "tf32"):
             raise ValueError("conv_kind must be 'f16' or 'tf32'")
         cfg.conv_kind = 0 if conv_kind == "f16" else 1
-        cfg.plane_handover = int(os.environ.get("DT_PLANE_HANDOVER", "3"))     # 0 = fp32 hand-over, 1 = conv1 -> conv2 as fp16 planes, 2 = also conv2 -> conv3, 3 = also image -> stem and pool -> first bottleneck
+        cfg.plane_handover = int(os.environ.get("DT_PLANE_HANDOVER", "3"))     # 0 = fp32 hand-over, 1 = conv1 -> conv2 as fp16 planes, 2 = also conv2 -> conv3, 3 = also image -> stem; 4 = also pool -> first bottleneck (measured: no net gain, opt-in)
         self.cfg = cfg
         self.h = self.L.dt_engine_create(ctypes.byref(cfg))
         if not self.h:

@@ -190,7 +190,8 @@ typedef struct dt_engine_config {
                                     activation >= 65504 raises the int32 buffer "range_flag"), 1 = 3xTF32 (no range limit) */
     int plane_handover;          /* kind::f16 only: 1 = conv1 of every bottleneck writes its output as two fp16 planes (hi, lo) that conv2 (3x3)
                                     loads straight into its operand tiles (no per-tap re-conversion); 2 = conv2 -> conv3 as well; 3 = also the
-                                    packed image -> stem and the pooled map -> first bottleneck (FPN engine); 0 = fp32 hand-over */
+                                    packed image -> stem (FPN engine); 4 = also the pooled map -> first bottleneck (no net gain measured:
+                                    opt-in); 0 = fp32 hand-over */
 } dt_engine_config;
 
 typedef void* dt_engine_t;
