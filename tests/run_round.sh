@@ -15,3 +15,5 @@ DT_NCU_REGION=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_dur
 echo "ncu launches exit=$?"; wc -l gpurun_out/r02_launches_dram_final.csv
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:roi_align_smem_map_kernel --launch-count 2 -o gpurun_out/r02_prof_roialign python tests/bench_micro.py roialign > gpurun_out/ncu_roi.log 2>&1
 echo "ncu roialign exit=$?"; ls -la gpurun_out/*.ncu-rep | tail -3
+DT_NCU_REGION=1 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_tcgen05_kernel --launch-count 16 -o gpurun_out/r02_prof_conv $B --steps 1 --warmup 3 > gpurun_out/ncu_full.log 2>&1
+echo "ncu conv exit=$?"; ls -la gpurun_out/*.ncu-rep | tail -3
