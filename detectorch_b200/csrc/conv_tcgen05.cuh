@@ -53,6 +53,12 @@ namespace dt {
 
 enum ConvResidualMode { RES_NONE = 0, RES_TILE = 1, RES_UPSAMPLE2X = 2 };
 enum ConvKind { KIND_TF32X3 = 0, KIND_F16X3 = 1 };
+#ifndef DT_INPLACE_RING
+#define DT_INPLACE_RING 1
+#endif
+#ifndef DT_INPLACE_NARROW
+#define DT_INPLACE_NARROW 1      // in-place fp16 split for the 64 / 128-wide fp32-input layers too (build switch kept for A/B)
+#endif
 #ifndef DT_CONV_WARPS_NARROW
 #define DT_CONV_WARPS_NARROW 4
 #endif
@@ -113,11 +119,14 @@ struct ConvCfg {
     // f16 : A (fp32 staging, 16 KB), A_h | A_l (8 KB each), B_h, B_l -- or, INPLACE, ONE 16 KB A area: TMA delivers the fp32 tile into
     //       it; the converter warps read their rows into registers, meet at a named barrier and write A_h | A_l IN PLACE over the fp32
     //       data (the two fp16 tiles are exactly as large as the fp32 tile); with a_planes TMA delivers A_h | A_l there directly.  A stage
-    //       is then 32 KB instead of 48 KB (5-6 pipeline stages instead of 3-4).  Same-box A/B (profiles/r02_summary.md): the deeper
-    //       pipeline gives -4..7 % on the long-K 256-wide layers (mask K-split convs, conv1 of layers 3-4, P2/P3 3x3, FC6), but the
-    //       extra barrier / the serialised read-then-write make the conversion-bound 64-wide layers and the epilogue-bound short-K layers
-    //       4-7 % slower: in place only for the long-K instantiations (256 wide, no ring, NMAIN = 1 or one epilogue slot).
-    static constexpr bool INPLACE = KIND == KIND_F16X3 && BLOCK_N == 256 && RING == 0 && (NMAIN == 1 || SLOTS == 1);
+    //       is then 32 KB instead of 48 KB (5-6 pipeline stages instead of 3-4).  Used by every non-ring, non-halo kind::f16 instantiation
+    //       but the 256-wide merged-accumulator ones with two staging slots.  History: with the round-2-start epilogue the deeper
+    //       pipeline only paid on the long-K 256-wide layers (-4..7 %) and cost the 64-wide / short-K layers 4-7 % (the extra converter
+    //       barrier sat on a chain the epilogue dominated); after the epilogue rewrite the 64 / 128-wide fp32-input layers (conv1 of
+    //       layers 1-2, RPN heads, mask logits) turned out to be bound by BYTES IN FLIGHT -- 3 stages x 16 KB per SM = 7 MB against the
+    //       ~10 MB that 6.5 TB/s x 1.5 us need -- and gained 6-12 % from the 6-deep in-place pipeline (profiles/r02_summary.md).
+    static constexpr bool INPLACE = KIND == KIND_F16X3 && (RING == 0 || DT_INPLACE_RING != 0) && HALO == 0 &&
+                                    (BLOCK_N == 256 ? (NMAIN == 1 || SLOTS == 1) : (DT_INPLACE_NARROW != 0 && DT_CONV_WARPS_NARROW == 4));
     static_assert(!HALO || (KIND == KIND_F16X3 && RING == 0 && !INPLACE), "the halo variant is a kind::f16, plane-input, no-ring kernel");
     static constexpr int HALO_ROWS = 160;                            // (8 + 2) x 16 pixel rows of 64 B per plane (HALO == 2: 8 x (16 + 3) = 152)
     static constexpr int HALO_PLANE_BYTES = HALO_ROWS * 64;          // 10 KB, a multiple of the 512-byte swizzle atom
