@@ -320,11 +320,14 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
     L->nmain = (bn == 64) ? (narrow1 ? 1 : 3) : ((bn == 128 && s.precise) ? 3 : ((bn == 256 && !s.no_merge && conv_merge_acc(p.ntaps * p.cin_blocks)) ? 0 : 1));
     finish_grid(L, ceil_div(s.Cout, bn));
     {
-        static int use_ring = -1;
-        if (use_ring < 0) { const char* e = getenv("DT_CONV_RES_RING"); use_ring = e ? atoi(e) : 1; }
-        // measured: -15..26 % on the K <= 256 residual layers (conv3 of the 64/128/256-channel stages), +11 % on K = 512 (two pipeline
-        // stages are too few for 16 k-blocks per tile)
-        L->ring = (use_ring && L->nmain == 0 && L->two_sm && L->kind == KIND_F16X3 && s.res_mode == RES_TILE && p.ntaps * p.cin_blocks <= 8) ? 1 : 0;
+        static int use_ring = -1, ring_kb = 8, ring2_kb = 0;
+        if (use_ring < 0) {
+            const char* e = getenv("DT_CONV_RES_RING"); use_ring = e ? atoi(e) : 1;
+            const char* e1 = getenv("DT_CONV_RING_KB"); if (e1) ring_kb = atoi(e1);             // ring for at most this many k-blocks per tile
+            const char* e2 = getenv("DT_CONV_RING2_KB"); if (e2) ring2_kb = atoi(e2);           // from this many k-blocks on: 2 ring tiles (one more stage)
+        }
+        L->ring = (use_ring && L->nmain == 0 && L->two_sm && L->kind == KIND_F16X3 && s.res_mode == RES_TILE && p.ntaps * p.cin_blocks <= ring_kb) ? 1 : 0;
+        if (L->ring && ring2_kb > 0 && p.ntaps * p.cin_blocks >= ring2_kb) L->ring = 2;
     }
     {
         // Two staging slots per epilogue group (the TMA store of a chunk drains while the next chunk is computed) for tiles up to 128 wide,
@@ -477,7 +480,7 @@ inline cudaError_t conv_launch_sm(const ConvLayer& L, cudaStream_t stream) {
                     if (L.ring) {
                         // residual prefetch ring: 2 tiles in flight per epilogue group with two staging slots (3 with one slot);
                         // ring 3 + 2 slots (possible with 32 KB stages) measured 8-11 % slower than ring 2 + 2 slots
-                        if (!s2) return conv_launch_cfg<256, 0, TWO, KIND, 3, 1>(L, stream);
+                        if (!s2) return L.ring == 2 ? conv_launch_cfg<256, 0, TWO, KIND, 2, 1>(L, stream) : conv_launch_cfg<256, 0, TWO, KIND, 3, 1>(L, stream);
                         return conv_launch_cfg<256, 0, TWO, KIND, 2, 2>(L, stream);
                     }
                     if (s2) return conv_launch_cfg<256, 0, TWO, KIND, 0, 2>(L, stream);
