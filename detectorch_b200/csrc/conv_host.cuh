@@ -320,7 +320,10 @@ inline bool conv_build(const ConvSpec& s, ConvLayer* L) {
     L->nmain = (bn == 64) ? (narrow1 ? 1 : 3) : ((bn == 128 && s.precise) ? 3 : ((bn == 256 && !s.no_merge && conv_merge_acc(p.ntaps * p.cin_blocks)) ? 0 : 1));
     finish_grid(L, ceil_div(s.Cout, bn));
     {
-        static int use_ring = -1, ring_kb = 8, ring2_kb = 0;
+        // Residual prefetch ring for the conv3 + residual layers (K <= 512): -15..26 % at K <= 256 when it was introduced; K = 512 (16 k-blocks
+        // per tile) was 11 % slower with it while a ring kernel had two 48 KB pipeline stages -- with in-place 32 KB stages it gains 15 %
+        // with 3 ring tiles / 3 stages and 23 % with 2 ring tiles / 4 stages (same-box sweep over DT_CONV_RING_KB / DT_CONV_RING2_KB).
+        static int use_ring = -1, ring_kb = 16, ring2_kb = 16;
         if (use_ring < 0) {
             const char* e = getenv("DT_CONV_RES_RING"); use_ring = e ? atoi(e) : 1;
             const char* e1 = getenv("DT_CONV_RING_KB"); if (e1) ring_kb = atoi(e1);             // ring for at most this many k-blocks per tile
