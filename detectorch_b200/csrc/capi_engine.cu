@@ -1020,6 +1020,8 @@ int dt_engine_run(dt_engine_t h, const float* image_nchw, float scaling_factor, 
     e->image = image_nchw;
     e->scaling_factor = scaling_factor;
     cudaStream_t st = (cudaStream_t)stream;
+    // a run from the first stage reports ITS OWN range flag (it used to stay raised until someone read it through Engine.check_range)
+    if (first_stage <= ST_TRUNK && cudaMemsetAsync(e->buf<int>("range_flag"), 0, sizeof(int), st) != cudaSuccess) return 0;
     for (const Op& op : e->ops) {
         if (op.stage < first_stage || op.stage > last_stage) continue;
         cudaError_t err = op.kind == 0 ? conv_launch(op.conv, st) : e->fns[op.fn](e, st);

@@ -187,7 +187,8 @@ typedef struct dt_engine_config {
     int use_rpn;                 /* 1 = Faster/Mask R-CNN (RPN head + proposal generation on the device), 0 = Fast R-CNN with pre-computed
                                     proposals (eval_fast.ipynb / eval_fast_FPN.ipynb): the caller fills `rois` (+ `roi_levels` for FPN), `roi_counts` */
     int conv_kind;               /* 0 = three-term product on the kind::f16 pipe (fp16 hi/lo halves, default: twice the tf32 issue rate; an
-                                    activation >= 65504 raises the int32 buffer "range_flag"), 1 = 3xTF32 (no range limit) */
+                                    activation >= 65504 raises the int32 buffer "range_flag", which every run that starts at the first stage clears
+                                    before it launches anything), 1 = 3xTF32 (no range limit) */
     int plane_handover;          /* kind::f16 only: 1 = conv1 of every bottleneck writes its output as two fp16 planes (hi, lo) that conv2 (3x3)
                                     loads straight into its operand tiles (no per-tap re-conversion); 2 = conv2 -> conv3 as well; 3 = also the
                                     packed image -> stem (FPN engine); 4 = also the pooled map -> first bottleneck (no net gain measured:
