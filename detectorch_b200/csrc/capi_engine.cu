@@ -536,14 +536,23 @@ cudaError_t fn_p6(Engine* e, cudaStream_t s) {
 // Proposal generation: the keys / two-level radix select / ordered compaction of every (level, image) run at full-GPU width
 // (rpn_select_*_kernel, one CTA per 4096 anchors), then one CTA per (level, image) sorts the ~1000 selected candidates, decodes, clips,
 // filters and runs the NMS.  DT_RPN_SPLIT=0 keeps the whole level in that one CTA (the round-1 kernel; P2's 182 400 anchors were its long pole).
-cudaError_t launch_proposals(Engine* e, cudaStream_t s, int levels) {
-    static int split = -1;
+// which of the two splits a proposal launch uses (also what dt_engine_count_launches reports before the first run)
+void rpn_modes(Engine* e, int levels) {
+    static int split = -1, nms_split = -1;
     if (split < 0) { const char* v = getenv("DT_RPN_SPLIT"); split = (v && v[0] == '0') ? 0 : 1; }
+    if (nms_split < 0) { const char* v = getenv("DT_RPN_NMS_SPLIT"); nms_split = (v && v[0] == '0') ? 0 : 1; }
     RpnParams& P = e->rpn;
-    P.scaling_factor = e->scaling_factor;
     int max_n = 0;
     for (int l = 0; l < levels; ++l) max_n = std::max(max_n, P.lv[l].n);
     P.split = (split && max_n <= kRpnChunk * kRpnMaxChunks) ? 1 : 0;
+    P.nms_split = (nms_split && P.pre_nms <= 8192 && P.nms_thresh > 0.f) ? 1 : 0;
+}
+cudaError_t launch_proposals(Engine* e, cudaStream_t s, int levels) {
+    RpnParams& P = e->rpn;
+    P.scaling_factor = e->scaling_factor;
+    rpn_modes(e, levels);
+    int max_n = 0;
+    for (int l = 0; l < levels; ++l) max_n = std::max(max_n, P.lv[l].n);
     if (P.split) {
         cudaError_t err = cudaMemsetAsync(P.sel_hist, 0, (size_t)e->cfg.batch * levels * 4096 * sizeof(uint32_t), s);
         if (err != cudaSuccess) return err;
@@ -553,9 +562,6 @@ cudaError_t launch_proposals(Engine* e, cudaStream_t s, int levels) {
         rpn_select_count_kernel<<<grid, 1024, 0, s>>>(P);
         rpn_select_scatter_kernel<<<grid, 1024, 0, s>>>(P);
     }
-    static int nms_split = -1;
-    if (nms_split < 0) { const char* v = getenv("DT_RPN_NMS_SPLIT"); nms_split = (v && v[0] == '0') ? 0 : 1; }
-    P.nms_split = (nms_split && P.pre_nms <= 8192 && P.nms_thresh > 0.f) ? 1 : 0;
     rpn_proposals_kernel<<<dim3(levels, e->cfg.batch), 1024, 0, s>>>(P);
     if (P.nms_split) {
         // DT_RPN_NMS_SPLIT=0 keeps the NMS inside rpn_proposals_kernel (one CTA per (level, image) sweeping every candidate over the survivors)
@@ -1071,6 +1077,7 @@ int dt_engine_profile(dt_engine_t h, const float* image_nchw, float scaling_fact
 int dt_engine_count_launches(dt_engine_t h, int first_stage, int last_stage) {
     Engine* e = reinterpret_cast<Engine*>(h);
     int n = 0;
+    if (e->cfg.use_rpn) rpn_modes(e, e->rpn.num_levels);
     for (const Op& op : e->ops)
         if (op.stage >= first_stage && op.stage <= last_stage)
             n += (op.kind == 1 && e->fns[op.fn] == fn_detect) ? 2 : ((op.kind == 1 && op.stage == ST_PROPOSALS) ? ((e->rpn.split ? 5 : 1) + (e->rpn.nms_split ? 2 : 0)) : 1);

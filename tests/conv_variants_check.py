@@ -53,6 +53,8 @@ def main():
     torch.cuda.synchronize()
     out["mask_logit_abs"] = ab(eng.buffer("mask_logits")[:D, :, :, :81].permute(0, 3, 1, 2), S["mask_logits"])
     out["range_flag"] = int(eng.buffer("range_flag").item())
+    # un-forced proposals / detections of the first run (the proposal kernels have switches too)
+    out["launches"] = eng.count_launches()
     print(json.dumps(out))
 
 
