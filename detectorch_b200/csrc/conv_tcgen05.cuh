@@ -30,20 +30,22 @@
 // BLOCK_K = 32 fp32 = one 128-byte swizzle row.
 //
 // Execution model (round-1 profile: the one-tile-per-CTA version lost ~20k cycles per tile to prologue +
-// un-overlapped epilogue): PERSISTENT CTAs in 2-CTA clusters, 448 threads =
-//   warp 0      TMA producer (A tile; its half of the weight k-block, multicast to both CTAs of the pair)
-//   warp 1      TMEM owner + MMA issuer (one elected lane)
-//   warps 2-5   A_lo converters
-//   warps 6-13  epilogue, two independent groups of 4 warps: TMEM -> regs -> scale/shift [+residual] [ReLU|sigmoid] ->
-//               swizzled smem -> TMA store, 32-channel chunks (even chunks group 0, odd chunks group 1), each group with
-//               its own 16 KB staging slot that is NOT aliased with the pipeline, so the producer / converter / MMA warps
-//               run ahead into the next tile while a tile drains.
+// un-overlapped epilogue): PERSISTENT CTAs in 2-CTA clusters, 512 threads =
+//   warp 0       TMA producer (A tile; its half of the weight k-block, multicast to both CTAs of the pair)
+//   warp 1       TMEM owner + MMA issuer (one elected lane)
+//   warps 2-5    operand converters (fp32 -> fp16 hi/lo, in place for most instantiations; pass-through for plane inputs)
+//   warps 6-13   epilogue WORKERS, two independent groups of 4 warps: TMEM -> regs -> scale/shift [+residual] [ReLU|sigmoid] ->
+//                swizzled staging slot, 32-channel chunks (even chunks group 0, odd chunks group 1); the staging slots are NOT
+//                aliased with the pipeline, so the producer / converter / MMA warps run ahead into the next tile while a tile drains
+//   warps 14-15  one STORE warp per group: TMA store of the staged chunk, tile bookkeeping, residual-ring refill, slot hand-back
+//                (arrive/sync named-barrier pair with the workers)
 // TMEM holds NMAIN rotating main-term accumulators + 1 cross-term accumulator per tile (NMAIN == 0: a single accumulator for
-// both, used by the short-K 256-wide layers), double-buffered when two tiles fit in the 512 columns.
+// both, used by the 256-wide layers up to K = 2304), double-buffered when two tiles fit in the 512 columns.
 // Variants selected by the host per layer (conv_host.cuh): 1-SM MMA with multicast weights vs cta_group::2, a K-split over filter
-// taps (tap0 / ntaps), and RING > 0: a ring of residual tiles prefetched by TMA for the short-K residual layers.
-// SLOTS: staging slots per epilogue group (1 or 2, picked per layer by the host).  DT_CONV_WARPS_NARROW (8 converter warps) is a
-// measured-and-rejected experiment switch.
+// taps (tap0 / ntaps), RING > 0: a ring of residual tiles prefetched by TMA for the conv3 + residual layers, SLOTS: staging slots per
+// epilogue group, HALO: 3x3 / stem forms that fetch one A box per filter row (row parity) and address the taps through shifted
+// UMMA descriptors, WS: weights resident in shared memory (stem).  DT_CONV_WARPS_NARROW (8 converter warps) is a
+// measured-and-rejected experiment switch; DT_INPLACE_NARROW / DT_INPLACE_RING are build switches kept for A/B.
 #pragma once
 #include <cuda_fp16.h>
 
